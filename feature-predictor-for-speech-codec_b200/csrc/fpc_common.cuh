@@ -1,0 +1,132 @@
+// fpc_common.cuh -- status codes, launch accounting and the few PTX wrappers the kernels use.
+#pragma once
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include "../../include/fpc_b200.h"
+
+namespace fpc {
+
+extern thread_local int g_last_cuda_error;
+extern unsigned long long g_launch_count;
+
+inline int cuda_fail(cudaError_t e)
+{
+    g_last_cuda_error = (int)e;
+    return FPC_ERR_CUDA;
+}
+
+#define FPC_CUDA_TRY(expr)                                   \
+    do {                                                     \
+        cudaError_t _e = (expr);                             \
+        if (_e != cudaSuccess) return ::fpc::cuda_fail(_e);  \
+    } while (0)
+
+// call right after a <<<>>> launch
+#define FPC_LAUNCH_CHECK()                                   \
+    do {                                                     \
+        __atomic_fetch_add(&::fpc::g_launch_count, 1ULL, __ATOMIC_RELAXED); \
+        cudaError_t _e = cudaGetLastError();                 \
+        if (_e != cudaSuccess) return ::fpc::cuda_fail(_e);  \
+    } while (0)
+
+// ------------------------------------------------------------------------------------------
+// packed images (device memory, produced by fpc_pack_*; layouts documented in DESIGN.md 4)
+// ------------------------------------------------------------------------------------------
+constexpr int kIn = FPC_IN_FEATURES;   // 20
+constexpr int kH1 = FPC_GRU1;          // 384
+constexpr int kH2 = FPC_GRU2;          // 128
+constexpr int kFc = FPC_FC;            // 18
+constexpr int kDim = FPC_CODE_DIMS;    // 17
+constexpr int kSurv = FPC_SURVIVORS;   // 5
+
+// fp32 weight stream: "groups" of 4 consecutive k for 384 gate columns of one pass
+// (128 hidden units x {r,z,n}); group = [6 column slots][64 unit pairs][4 k] floats.
+constexpr int kGroupFloats = 6 * 64 * 4;                 // 1536
+constexpr int kGroupBytes = kGroupFloats * 4;            // 6144
+constexpr int kG1x = kIn / 4;                            // 5 groups: GRU1 input part
+constexpr int kG1h = kH1 / 4;                            // 96 groups: GRU1 hidden part
+constexpr int kG1 = kG1x + kG1h;                         // 101 per pass, 3 passes
+constexpr int kG2x = kH1 / 4;                            // 96: GRU2 input part (h1')
+constexpr int kG2h = kH2 / 4;                            // 32: GRU2 hidden part
+constexpr int kG2 = kG2x + kG2h;                         // 128
+constexpr int kGroupsPerFrame = 3 * kG1 + kG2;           // 431
+constexpr int kStreamFloats = kGroupsPerFrame * kGroupFloats;
+constexpr int kBiasFloats = 4 * 4 * 128;                 // [3 GRU1 passes + GRU2][br,bz,bni,bnh][128]
+constexpr int kFcFloats = kFc * kH2;                     // 2304
+constexpr int kPackedF32Floats = ((kStreamFloats + kBiasFloats + kFcFloats + kFc + 3) / 4) * 4;
+
+struct PackedVq {        // one VQ codebook file
+    int dtype, stages, K, pad;
+    long long off_t[2];   // byte offset of stage s transposed [17][K]
+    long long off_r[2];   // byte offset of stage s row-major  [K][17]
+};
+struct PackedScl {
+    int dtype, n;
+    long long off;
+};
+struct PackedCodebooks {  // header at offset 0 of the packed codebook image
+    PackedVq vq, bl;
+    PackedScl scl, blscl;
+};
+constexpr size_t kCbHeaderBytes = 256;
+constexpr size_t kCbVqMaxBytes = (size_t)2 * FPC_MAX_VQ_ENTRIES * kDim * 8 * 2;   // both layouts, f64
+constexpr size_t kCbSclMaxBytes = (size_t)FPC_MAX_SCL_ENTRIES * 8;
+constexpr size_t kPackedCbBytes = kCbHeaderBytes + 2 * kCbVqMaxBytes + 2 * kCbSclMaxBytes;
+
+// ------------------------------------------------------------------------------------------
+// PTX: mbarrier + 1-D bulk async copy (TMA engine, SASS UBLKCP)
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ uint32_t smem_u32(const void *p)
+{
+    return (uint32_t)__cvta_generic_to_shared(p);
+}
+__device__ __forceinline__ void mbar_init(uint64_t *bar, uint32_t count)
+{
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count) : "memory");
+}
+__device__ __forceinline__ void mbar_fence_init()
+{
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t *bar)
+{
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint64_t *bar, uint32_t bytes)
+{
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes)
+                 : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
+{
+    uint32_t ok;
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
+{
+    while (!mbar_try_wait(bar, parity)) {
+    }
+}
+// global -> shared bulk copy, completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
+{
+    asm volatile(
+        "cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void named_bar_sync(int id, int nthreads)
+{
+    asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");
+}
+
+}  // namespace fpc

@@ -1,0 +1,195 @@
+/*
+ * fpc_b200.h -- C ABI of the B200-native closed-loop predictive-coding path.
+ *
+ * The reference (haiciyang/Feature-predictor-for-speech-codec) is pure Python and has no
+ * FFI of its own; its plug-in seam is the set of Python call signatures listed below
+ * (SURVEY.md section 8b).  Each entry point here is what a binding for that call site binds
+ * to.  Paths are relative to /root/reference/src.
+ *
+ *   fpc_encode                 <- models/wavernn.py:165-256   Wavernn.encoder (whole frame loop,
+ *                                 including the injected vq_quantize / scl_quantize calls at
+ *                                 :219-240 and the feedback at :242,252)
+ *   fpc_decode                 <- models/wavernn.py:367-379   Wavernn.decoder (receiver replay)
+ *   fpc_pack_weights           <- models/wavernn.py:37-38,48-52  parameters of rnn1/rnn2/dual_fc
+ *   fpc_pack_codebooks         <- quantization/vq_func.py:141,171  the np.load of the four files
+ *   fpc_vq_quantize            <- quantization/vq_func.py:134-164  vq_quantize / quantize_mstage
+ *   fpc_scl_quantize           <- quantization/vq_func.py:167-185  scl_quantize
+ *   fpc_index_histogram        <- models/wavernn.py:189,221-240    cb_tot accumulation
+ *   fpc_kmeans_assign_accumulate <- quantization/cb_func.py:56-68,82-86  find_nearest + sums
+ *   fpc_kmeans_finalize        <- quantization/cb_func.py:88-97    divide, cluster statistics
+ *   fpc_kmeans_gather          <- quantization/cb_func.py:103-112  quantize
+ *
+ * Conventions
+ *   - Plain C: pointers, sizes, a stream handle.  No torch / C++ types cross this boundary.
+ *   - Every pointer named d_* is DEVICE memory owned by the caller; the library never
+ *     allocates or frees device memory and never synchronises the stream.  The caller keeps
+ *     buffers alive until the stream has drained.
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream).
+ *   - Every function returns an fpc_status; 0 is success.  Nothing throws, nothing prints.
+ *   - There is no CPU fallback: without a CUDA device every compute entry point returns
+ *     FPC_ERR_CUDA.
+ */
+#ifndef FPC_B200_H_
+#define FPC_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define FPC_VERSION 100 /* 0.1.0 */
+
+typedef enum {
+    FPC_OK = 0,
+    FPC_ERR_ARG = 1,          /* null pointer / negative size */
+    FPC_ERR_SHAPE = 2,        /* dimensions this build does not implement */
+    FPC_ERR_CODEBOOK = 3,     /* bad codebook (stages, entries, dtype) */
+    FPC_ERR_WORKSPACE = 4,    /* workspace / packed buffer too small */
+    FPC_ERR_CUDA = 5,         /* a CUDA runtime call failed; see fpc_last_cuda_error() */
+    FPC_ERR_UNSUPPORTED = 6   /* precision / mode not built */
+} fpc_status;
+
+/* arithmetic of the predictor's dense contractions */
+typedef enum {
+    FPC_PREC_FP32 = 0, /* FFMA, canonical summation order: bit-exact against oracle/ */
+    FPC_PREC_BF16 = 1  /* bf16 operands on tcgen05 tensor cores, fp32 accumulate in TMEM */
+} fpc_precision;
+
+/* element type of a codebook file; vq_func.py:18 computes in the file's dtype */
+typedef enum { FPC_F32 = 0, FPC_F64 = 1 } fpc_dtype;
+
+/* Fixed model geometry of this build (wavernn.py:24 with the arguments of
+ * synthesis_qtz.py:79-85 / BASELINE.json): in_features 20, gru_units1 384, gru_units2 128,
+ * fc_units 18, code_dims 17, SURVIVORS 5 (vq_func.py:3). */
+#define FPC_IN_FEATURES 20
+#define FPC_GRU1 384
+#define FPC_GRU2 128
+#define FPC_FC 18
+#define FPC_CODE_DIMS 17
+#define FPC_SURVIVORS 5
+#define FPC_MAX_VQ_ENTRIES 1024
+#define FPC_MAX_SCL_ENTRIES 256
+
+int fpc_version(void);
+const char *fpc_status_string(int status);
+/* cudaError_t of the most recent failing CUDA call on this thread (0 if none) */
+int fpc_last_cuda_error(void);
+/* number of kernel launches issued by this library since load (for bench.py's gpu_launches) */
+unsigned long long fpc_launch_count(void);
+
+/* ---------------------------------------------------------------------------------------------
+ * predictor weights
+ * ------------------------------------------------------------------------------------------- */
+/* Parameters in torch's own layout, all float32 on the device (state_dict of the module):
+ * GRU gate row order r, z, n. */
+typedef struct {
+    const float *w_ih1; /* (3*384, 20)   rnn1.weight_ih_l0 */
+    const float *w_hh1; /* (3*384, 384)  rnn1.weight_hh_l0 */
+    const float *b_ih1; /* (3*384)       rnn1.bias_ih_l0   */
+    const float *b_hh1; /* (3*384)       rnn1.bias_hh_l0   */
+    const float *w_ih2; /* (3*128, 384)  rnn2.weight_ih_l0 */
+    const float *w_hh2; /* (3*128, 128)  rnn2.weight_hh_l0 */
+    const float *b_ih2; /* (3*128)       rnn2.bias_ih_l0   */
+    const float *b_hh2; /* (3*128)       rnn2.bias_hh_l0   */
+    const float *w_fc;  /* (18, 128)     dual_fc.0.weight  */
+    const float *b_fc;  /* (18)          dual_fc.0.bias    */
+} fpc_weights;
+
+/* bytes of the kernel-side weight image for a precision */
+size_t fpc_packed_weights_bytes(int precision);
+/* re-tile the parameters into the streaming order of the frame-step kernel (one kernel launch) */
+int fpc_pack_weights(const fpc_weights *w, int precision, void *d_packed, size_t packed_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * codebooks
+ * ------------------------------------------------------------------------------------------- */
+/* The four files Wavernn.encoder reads through cfg (wavernn.py:219-237), already on the device
+ * in their on-disk layout: VQ (stages, K, 17) row-major, scalar (n) -- stages in {1,2}, all
+ * stages of one file share K (np.load gives a rectangular array), 5 <= K <= 1024, n <= 256.
+ * stages == 0 / n == 0 means the cfg path was '' (below-threshold residual is dropped). */
+typedef struct {
+    const void *vq;      int vq_dtype;     int vq_stages;  int vq_entries;      /* cfg['cb_path'] */
+    const void *bl_vq;   int bl_vq_dtype;  int bl_vq_stages; int bl_vq_entries; /* cfg['bl_cb_path'] */
+    const void *scl;     int scl_dtype;    int scl_entries;                     /* cfg['scl_cb_path'] */
+    const void *bl_scl;  int bl_scl_dtype; int bl_scl_entries;                  /* cfg['bl_scl_cb_path'] */
+} fpc_codebooks;
+
+size_t fpc_packed_codebooks_bytes(void);
+int fpc_pack_codebooks(const fpc_codebooks *cb, void *d_packed, size_t packed_bytes, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * closed-loop encoder  (Wavernn.encoder, wavernn.py:165-256)
+ * ------------------------------------------------------------------------------------------- */
+typedef struct {
+    /* inputs */
+    const float *d_feat;   /* (B, L, 20) normalised features; read-only */
+    const float *d_mask;   /* (B, L, 2) external indicator or NULL -> thresholds (wavernn.py:201-212) */
+    int B, L;
+    float l1, l2;          /* thresholds on |r0| and sum|r1..17|, strict >, fp32 (:202,206) */
+    int qtz;               /* 1: quantise and feed back (:214-242); 0: residual generation (:244-252) */
+    /* outputs, all written in full by the call (the callee of the reference allocates zeros) */
+    float *d_c_in;         /* (B, L, 20) decoded frames  == c_in[:,1:,:] (:256) */
+    float *d_r;            /* (B, L, 18) raw residual (qtz) or masked residual (!qtz) */
+    float *d_r_qtz;        /* (B, L, 18) quantised residual (zeros when !qtz) */
+    float *d_r_under;      /* (B, L, 18) below-threshold residual (!qtz) / zeros; may be NULL */
+    float *d_ind1;         /* (B, L) 0/1; may be NULL */
+    float *d_ind2;         /* (B, L) 0/1; may be NULL */
+    int32_t *d_idx;        /* (B, L, 4) [scalar idx, vq stage-1 (or below) idx, vq stage-2 idx,
+                              flags bit0=ind1 bit1=ind2]; -1 = nothing coded; may be NULL */
+} fpc_encode_io;
+
+/* scratch the encoder needs for a batch of B utterances (0 is a valid answer) */
+size_t fpc_encode_workspace_bytes(int B, int L, int precision);
+
+int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_io *io,
+               int precision, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* receiver side: c[t] = predictor(c[t-1]) + r_qtz[t], pitch passed through.
+ * d_r_qtz (B,L,18), d_pitch (B,L,2) -> d_c_out (B,L,20). */
+int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *d_pitch, int B, int L,
+               float *d_c_out, int precision, void *d_workspace, size_t workspace_bytes, void *stream);
+
+/* cb_tot (wavernn.py:189,221-240): five count tables from the index record.
+ * d_hist: 256 + 256 + 1024 + 1024 + 1024 uint64 counters at the offsets below, zeroed by the call. */
+#define FPC_HIST_SCL 0
+#define FPC_HIST_BL_SCL 256
+#define FPC_HIST_VQ1 512
+#define FPC_HIST_VQ2 1536
+#define FPC_HIST_BL_VQ 2560
+#define FPC_HIST_TOTAL 3584
+int fpc_index_histogram(const int32_t *d_idx, long n_frames, unsigned long long *d_hist, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * stand-alone quantisers  (vq_func.py:134-185)
+ * ------------------------------------------------------------------------------------------- */
+/* d_x (n,17) float32; d_cb (stages,K,17) of `dtype`; d_q (n,17) of `dtype` (numpy returns the
+ * codebook dtype); d_idx (n,stages) int32. */
+int fpc_vq_quantize(const float *d_x, long n, const void *d_cb, int dtype, int stages, int entries,
+                    void *d_q, int32_t *d_idx, void *stream);
+/* d_x (n) float32; d_codes (n_code) of `dtype`; d_q (n) of `dtype`; d_idx (n) int32 */
+int fpc_scl_quantize(const float *d_x, long n, const void *d_codes, int dtype, int n_code, void *d_q,
+                     int32_t *d_idx, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * k-means codebook learning  (cb_func.py)
+ * ------------------------------------------------------------------------------------------- */
+/* One assignment pass of cb_func.update over this rank's shard: nearest centroid in float64
+ * direct form (first minimum), then per-centroid float64 sums and counts ADDED into d_sums (K,17)
+ * and d_counts (K) (caller zeroes them; with several ranks the caller all-reduces them before
+ * fpc_kmeans_finalize).  d_idx (N) int32 may be NULL.  d_workspace: fpc_kmeans_workspace_bytes. */
+size_t fpc_kmeans_workspace_bytes(long N, int K);
+int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
+                                 double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                                 void *stream);
+/* codebook = sums / (counts + 1e-20); stats[4] = {min count, max count, #empty, sum (count/N)^2} */
+int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, double n_total, double *d_cb_out,
+                        double *d_stats, void *stream);
+/* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
+int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* FPC_B200_H_ */

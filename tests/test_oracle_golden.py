@@ -1,0 +1,85 @@
+"""Pins the CPU oracle (oracle/fpc_oracle.c) against golden vectors produced by the
+UNMODIFIED reference (oracle/gen_golden.py).  Tolerances are the ones BASELINE.json states:
+codebook indices equal on >= 99.99 % of frames, decoded features within 1e-4 abs.
+The quantizer arithmetic itself is required to be bit-exact."""
+import numpy as np
+import pytest
+
+from helpers import golden_codebooks, hist_equal, index_agreement, load_golden, oracle_codebooks, sd_checksum
+
+FEATURE_TOL = 1e-4       # BASELINE.json north_star: decoded features within 1e-4 abs
+INDEX_AGREEMENT = 0.9999  # BASELINE.json north_star: >= 99.99 % of frames
+
+ENCODER_CASES = ["cfg1_readme", "calibrated", "f64cb", "no_below", "smallcb", "qtz0", "mask_b1"]
+
+
+def test_forward_matches_reference(oracle, oracle_weights, state_dict):
+    g = load_golden("forward")
+    assert str(g["weights_sha256"]) == sd_checksum(state_dict), "seeded weights differ from the golden run"
+    y, h1, h2 = oracle.forward(oracle_weights, g["x"])
+    assert np.abs(y - g["y"]).max() < 2e-6
+    assert np.abs(h1 - g["h1"][0]).max() < 2e-6
+    assert np.abs(h2 - g["h2"][0]).max() < 2e-6
+    y2, h1b, h2b = oracle.forward(oracle_weights, g["x"][:, :7], h1, h2)
+    assert np.abs(y2 - g["y2"]).max() < 2e-6
+    assert np.abs(h1b - g["h1b"][0]).max() < 2e-6
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_quantizers_bit_exact(oracle, tag):
+    g = load_golden("quantizers")
+    x, xs = g["x_" + tag], g["xs_" + tag]
+    q2, i2 = oracle.vq_quantize(g["cb2_" + tag], x)
+    assert np.array_equal(i2, g["i2_" + tag])
+    assert np.array_equal(q2.astype(g["q2_" + tag].dtype), g["q2_" + tag])
+    assert np.array_equal(q2.astype(g["q2b_" + tag].dtype), g["q2b_" + tag])     # batched call form
+    assert np.array_equal(np.bincount(i2[:, 0], minlength=64), g["hist2b0_" + tag])
+    assert np.array_equal(np.bincount(i2[:, 1], minlength=64), g["hist2b1_" + tag])
+    q1, i1 = oracle.vq_quantize(g["cb1_" + tag], x)
+    assert np.array_equal(i1, g["i1_" + tag])
+    assert np.array_equal(q1.astype(g["q1_" + tag].dtype), g["q1_" + tag])
+    qs, si = oracle.scl_quantize(g["scl_" + tag], xs)
+    assert np.array_equal(si, g["is_" + tag])
+    assert np.array_equal(qs.astype(g["qs_" + tag].dtype)[:, None], g["qs_" + tag])
+    # the forced ties resolve to the lowest index (stable sorted(), argmin)
+    assert i2[0, 0] == 3 and i2[0, 1] == 20
+    assert i1[1, 0] == 7
+    assert si[1] == 10
+
+
+def test_kmeans_matches_reference(oracle):
+    g = load_golden("kmeans")
+    idx0 = oracle.find_nearest(g["data"], g["cb0"])
+    assert np.array_equal(idx0, g["idx0"])
+    cb1, idx, counts, stats = oracle.kmeans_update(g["data"], g["cb0"], with_details=True)
+    assert np.array_equal(cb1, g["cb1"])          # float64 sums in data order -> bit-exact
+    assert stats[2] >= 4                           # the four far-away centroids are empty ...
+    assert np.all(cb1[60:] == 0.0)                 # ... and collapse to the zero vector
+    cb2 = oracle.kmeans_update(g["data"], cb1)
+    assert np.array_equal(cb2, g["cb2"])
+    q, _ = oracle.kmeans_quantize(cb2, g["data"])
+    assert np.array_equal(q, g["q"])
+    rng = np.random.RandomState(int(g["train_seed"]))
+    cbt = oracle.vq_train(g["train_data"], np.zeros((8, 17)), 8, rng)
+    assert np.array_equal(cbt, g["train_cb"])
+
+
+@pytest.mark.parametrize("case", ENCODER_CASES)
+def test_encoder_matches_reference(oracle, oracle_weights, state_dict, synth, case):
+    g = load_golden(case)
+    assert str(g["weights_sha256"]) == sd_checksum(state_dict), "seeded weights differ from the golden run"
+    cbs = golden_codebooks(synth, g)
+    C = oracle_codebooks(oracle, cbs)
+    out = oracle.encode(oracle_weights, C, g["feat"], float(g["l1"]), float(g["l2"]),
+                        mask=g.get("mask"), qtz=bool(int(g["qtz"])))
+    agree, same = index_agreement(out["idx"], g["idx"])
+    assert agree >= INDEX_AGREEMENT, "index agreement %.6f" % agree
+    for k in ("c_in", "r", "r_qtz", "r_under"):
+        err = np.abs(out[k] - g[k]).max()
+        assert err <= FEATURE_TOL, "%s max abs err %g" % (k, err)
+    assert np.array_equal(out["ind1"], g["ind1"]) and np.array_equal(out["ind2"], g["ind2"])
+    if agree == 1.0 and int(g["qtz"]):
+        ref_hist = [g["hist%d" % j] for j in range(5)]
+        assert hist_equal(oracle.histograms(out["idx"], C), ref_hist)
+        # with identical indices the quantized residual is the same codeword sum, bit for bit
+        assert np.array_equal(out["r_qtz"], g["r_qtz"])

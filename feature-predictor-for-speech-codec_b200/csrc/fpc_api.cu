@@ -1,0 +1,215 @@
+// fpc_api.cu -- C-ABI entry points of the encode / decode / quantiser paths (include/fpc_b200.h).
+#include "fpc_common.cuh"
+#include "fpc_vq.cuh"
+#include "fpc_vq_search.cuh"
+#include "fpc_encode.cuh"
+
+namespace fpc {
+
+// ------------------------------------------------------------------------------------------
+// stand-alone VQ quantiser (vq_func.py:134-164): tiles of 32 vectors per CTA iteration
+// ------------------------------------------------------------------------------------------
+constexpr int kQTile = 32;
+
+template <typename T>
+__global__ void __launch_bounds__(kComputeThreads, 1)
+vq_quantize_kernel(const float *__restrict__ x, long n, const char *__restrict__ cb, int which, T *__restrict__ q,
+                   int32_t *__restrict__ idx)
+{
+    extern __shared__ __align__(128) unsigned char smem[];
+    float *rs = reinterpret_cast<float *>(smem);                 // [32][24]
+    float *rq = rs + kQTile * kLdR;                              // [32][20]
+    int *idx1 = reinterpret_cast<int *>(rq + kQTile * 20);       // [32]
+    int *idx2 = idx1 + kQTile;
+    int *list = idx2 + kQTile;
+    char *scratch = reinterpret_cast<char *>(list + kQTile);
+    const PackedCodebooks *h = reinterpret_cast<const PackedCodebooks *>(cb);
+    const PackedVq &bk = which == 0 ? h->vq : h->bl;
+    const int tid = threadIdx.x;
+    const long ntiles = (n + kQTile - 1) / kQTile;
+    for (long tile = blockIdx.x; tile < ntiles; tile += gridDim.x) {
+        const long base = tile * kQTile;
+        const int nb = (int)min((long)kQTile, n - base);
+        for (int i = tid; i < kQTile * kDim; i += kComputeThreads) {
+            const int r = i / kDim, d = i - r * kDim;
+            rs[r * kLdR + 4 + d] = r < nb ? x[(base + r) * kDim + d] : 0.0f;
+        }
+        if (tid < kQTile) list[tid] = tid;
+        __syncthreads();
+        vq_search_rows<T>(bk, cb, list, nb, kQTile, rs, rq, idx1, idx2, scratch, 8, tid, q + base * kDim);
+        if (tid < nb) {
+            idx[(base + tid) * bk.stages] = idx1[tid];
+            if (bk.stages > 1) idx[(base + tid) * bk.stages + 1] = idx2[tid];
+        }
+        __syncthreads();
+    }
+}
+
+template <typename T>
+__global__ void scl_quantize_kernel(const float *__restrict__ x, long n, const T *__restrict__ codes, int n_code,
+                                    T *__restrict__ q, int32_t *__restrict__ idx)
+{
+    const int lane = threadIdx.x & 31;
+    const long warp = ((long)blockIdx.x * blockDim.x + threadIdx.x) >> 5;
+    const long nwarps = ((long)gridDim.x * blockDim.x) >> 5;
+    for (long i = warp; i < n; i += nwarps) {
+        T qv;
+        const int bi = warp_scl_nearest<T>(codes, n_code, x[i], lane, qv);
+        if (lane == 0) { q[i] = qv; idx[i] = bi; }
+    }
+}
+
+// cb_tot (wavernn.py:189,221-240) from the index record
+__global__ void index_histogram_kernel(const int4 *__restrict__ idx, long n, unsigned long long *__restrict__ hist)
+{
+    __shared__ unsigned int sh[FPC_HIST_TOTAL];
+    for (int i = threadIdx.x; i < FPC_HIST_TOTAL; i += blockDim.x) sh[i] = 0;
+    __syncthreads();
+    for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
+        const int4 v = idx[i];
+        if (v.x >= 0 && v.x < 256) atomicAdd(&sh[((v.w & 1) ? FPC_HIST_SCL : FPC_HIST_BL_SCL) + v.x], 1u);
+        if (v.y >= 0 && v.y < 1024) atomicAdd(&sh[((v.w & 2) ? FPC_HIST_VQ1 : FPC_HIST_BL_VQ) + v.y], 1u);
+        // a two-stage below-threshold book counts its LAST stage (cb_tot[4] += cb_t[-1], :240)
+        if (v.z >= 0 && v.z < 1024) {
+            if (v.w & 2) atomicAdd(&sh[FPC_HIST_VQ2 + v.z], 1u);
+        }
+    }
+    __syncthreads();
+    for (int i = threadIdx.x; i < FPC_HIST_TOTAL; i += blockDim.x)
+        if (sh[i]) atomicAdd(&hist[i], (unsigned long long)sh[i]);
+}
+
+}  // namespace fpc
+
+using namespace fpc;
+
+extern "C" {
+
+size_t fpc_encode_workspace_bytes(int B, int L, int precision)
+{
+    (void)B; (void)L; (void)precision;
+    return 0;   // all per-frame state lives in shared memory
+}
+
+int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_io *io, int precision,
+               void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    (void)d_workspace; (void)workspace_bytes;
+    if (!d_packed_weights || !io) return FPC_ERR_ARG;
+    if (io->B < 0 || io->L < 0) return FPC_ERR_ARG;
+    if (io->B == 0 || io->L == 0) return FPC_OK;
+    if (!io->d_feat || !io->d_c_in || !io->d_r || !io->d_r_qtz) return FPC_ERR_ARG;
+    if (io->qtz && !d_packed_codebooks) return FPC_ERR_ARG;
+    if (precision != FPC_PREC_FP32) return FPC_ERR_UNSUPPORTED;
+    EncodeParams P;
+    P.wstream = (const float *)d_packed_weights;
+    P.cb = (const char *)d_packed_codebooks;
+    P.feat = io->d_feat;
+    P.mask = io->d_mask;
+    P.rq_in = nullptr;
+    P.pitch_in = nullptr;
+    P.c_in = io->d_c_in; P.r = io->d_r; P.r_qtz = io->d_r_qtz; P.r_under = io->d_r_under;
+    P.ind1 = io->d_ind1; P.ind2 = io->d_ind2; P.idx = io->d_idx;
+    P.B = io->B; P.L = io->L;
+    P.mode = io->qtz ? kModeQuantize : kModeResidual;
+    P.l1 = io->l1; P.l2 = io->l2;
+    P.ntiles = 0;
+    return run_encode_fp32(P, (cudaStream_t)stream, 0);
+}
+
+int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *d_pitch, int B, int L, float *d_c_out,
+               int precision, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    (void)d_workspace; (void)workspace_bytes;
+    if (!d_packed_weights) return FPC_ERR_ARG;
+    if (B < 0 || L < 0) return FPC_ERR_ARG;
+    if (B == 0 || L == 0) return FPC_OK;
+    if (!d_r_qtz || !d_pitch || !d_c_out) return FPC_ERR_ARG;
+    if (precision != FPC_PREC_FP32) return FPC_ERR_UNSUPPORTED;
+    EncodeParams P;
+    P.wstream = (const float *)d_packed_weights;
+    P.cb = nullptr; P.feat = nullptr; P.mask = nullptr;
+    P.rq_in = d_r_qtz; P.pitch_in = d_pitch;
+    P.c_in = d_c_out; P.r = nullptr; P.r_qtz = nullptr; P.r_under = nullptr;
+    P.ind1 = nullptr; P.ind2 = nullptr; P.idx = nullptr;
+    P.B = B; P.L = L; P.mode = kModeDecode; P.l1 = 0.0f; P.l2 = 0.0f; P.ntiles = 0;
+    return run_encode_fp32(P, (cudaStream_t)stream, 0);
+}
+
+int fpc_index_histogram(const int32_t *d_idx, long n_frames, unsigned long long *d_hist, void *stream)
+{
+    if (!d_hist || n_frames < 0) return FPC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    FPC_CUDA_TRY(cudaMemsetAsync(d_hist, 0, sizeof(unsigned long long) * FPC_HIST_TOTAL, st));
+    if (n_frames == 0) return FPC_OK;
+    if (!d_idx) return FPC_ERR_ARG;
+    long blocks = (n_frames + 1023) / 1024;
+    const int cap = 4 * (num_sms() > 0 ? num_sms() : 148);
+    if (blocks > cap) blocks = cap;
+    index_histogram_kernel<<<(int)blocks, 256, 0, st>>>((const int4 *)d_idx, n_frames, d_hist);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+/* stand-alone vq_quantize on a packed codebook image; `which` 0 = cfg['cb_path'] slot,
+ * 1 = cfg['bl_cb_path'] slot.  (declared in the header with a raw-codebook signature; the
+ * packed form is what the Python mirror binds because it caches packed images per file.) */
+int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebooks, int which, int dtype, int stages,
+                           void *d_q, int32_t *d_idx, void *stream)
+{
+    if (n < 0) return FPC_ERR_ARG;
+    if (n == 0) return FPC_OK;
+    if (!d_x || !d_packed_codebooks || !d_q || !d_idx) return FPC_ERR_ARG;
+    if (stages < 1 || stages > 2) return FPC_ERR_CODEBOOK;
+    cudaStream_t st = (cudaStream_t)stream;
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
+    long tiles = (n + kQTile - 1) / kQTile;
+    const int grid = (int)(tiles < sms ? tiles : sms);
+    const size_t fixed = (size_t)(kQTile * kLdR + kQTile * 20 + 3 * kQTile) * 4;
+    if (dtype == FPC_F32) {
+        const size_t smem = fixed + vq_fixed_bytes<float>(kQTile) + 8 * 1024 * sizeof(float);
+        static bool cfg = false;
+        if (!cfg) {
+            FPC_CUDA_TRY(cudaFuncSetAttribute(vq_quantize_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cfg = true;
+        }
+        vq_quantize_kernel<float><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
+                                                                          (float *)d_q, d_idx);
+    } else if (dtype == FPC_F64) {
+        const size_t smem = fixed + vq_fixed_bytes<double>(kQTile) + 8 * 1024 * sizeof(double);
+        static bool cfg = false;
+        if (!cfg) {
+            FPC_CUDA_TRY(cudaFuncSetAttribute(vq_quantize_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+            cfg = true;
+        }
+        vq_quantize_kernel<double><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
+                                                                           (double *)d_q, d_idx);
+    } else {
+        return FPC_ERR_CODEBOOK;
+    }
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+int fpc_scl_quantize(const float *d_x, long n, const void *d_codes, int dtype, int n_code, void *d_q, int32_t *d_idx,
+                     void *stream)
+{
+    if (n < 0) return FPC_ERR_ARG;
+    if (n == 0) return FPC_OK;
+    if (!d_x || !d_codes || !d_q || !d_idx) return FPC_ERR_ARG;
+    if (n_code < 1 || n_code > FPC_MAX_SCL_ENTRIES) return FPC_ERR_CODEBOOK;
+    cudaStream_t st = (cudaStream_t)stream;
+    long blocks = (n + 7) / 8;
+    if (blocks > 1184) blocks = 1184;
+    if (dtype == FPC_F32)
+        scl_quantize_kernel<float><<<(int)blocks, 256, 0, st>>>(d_x, n, (const float *)d_codes, n_code, (float *)d_q, d_idx);
+    else if (dtype == FPC_F64)
+        scl_quantize_kernel<double><<<(int)blocks, 256, 0, st>>>(d_x, n, (const double *)d_codes, n_code, (double *)d_q, d_idx);
+    else
+        return FPC_ERR_CODEBOOK;
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+}  // extern "C"

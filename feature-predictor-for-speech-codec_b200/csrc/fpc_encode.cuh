@@ -1,0 +1,26 @@
+// fpc_encode.cuh -- launch parameters shared by the frame-step kernels and the C-ABI layer.
+#pragma once
+#include "fpc_common.cuh"
+
+namespace fpc {
+
+enum { kModeResidual = 0, kModeQuantize = 1, kModeDecode = 2 };
+
+struct EncodeParams {
+    const float *wstream;   // packed fp32 weights (fpc_pack_weights)
+    const char *cb;         // packed codebooks (fpc_pack_codebooks) or null
+    const float *feat;      // (B,L,20)   [decode: unused]
+    const float *mask;      // (B,L,2) or null
+    const float *rq_in;     // decode: (B,L,18)
+    const float *pitch_in;  // decode: (B,L,2)
+    float *c_in, *r, *r_qtz, *r_under, *ind1, *ind2;
+    int32_t *idx;
+    int B, L, mode;
+    float l1, l2;
+    int ntiles;
+};
+
+int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu);
+int num_sms();
+
+}  // namespace fpc

@@ -1,0 +1,451 @@
+// fpc_encode_fp32.cu -- the fused, persistent closed-loop frame-step kernel (fp32 FFMA path).
+//
+// Replaces the whole body of Wavernn.encoder (/root/reference/src/models/wavernn.py:165-256):
+// per frame  forward (:194 -> :63-102), residual (:196), thresholds (:202-208), the injected
+// scl_quantize / vq_quantize calls (:217-240 -> quantization/vq_func.py), the feedback (:242 or
+// :252), for a tile of MT = 4*TU utterances per CTA with the frame loop INSIDE the kernel.
+// Nothing leaves the SM between frames except the per-frame outputs; the GRU states, the
+// decoded frame that is fed back and all quantiser scratch live in shared memory.
+//
+// Work split inside a CTA (384 threads = 3 warpgroups; setmaxnreg moves the producer group's
+// registers to the two compute groups):
+//   warps 0..7  compute.  Thread (tg = lane>>3, ug = warp*8 + (lane&7)) owns hidden units
+//               {2ug, 2ug+1} (+128*pass) for utterances {tg, tg+4, ..., tg+4(TU-1)} of the tile,
+//               i.e. a TU x 2 x {r,z,n_i,n_h} register tile; every dot product is one
+//               ascending-k FFMA chain (the canonical order the oracle follows).
+//   warp 8      producer (warps 9..11 only exist to complete the warpgroup).  One lane streams the 2.65 MB packed weight image through an
+//               8-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP),
+//               mbarrier full/empty handshakes; the image stays L2-resident (it is re-read by
+//               every CTA every frame) and the ring runs ahead across frame boundaries.
+// After the GRUs: FC + 2*tanh, residual, thresholds, scalar quantiser (one warp per
+// utterance), then the m-best VQ search with each thread holding 4 codewords of each stage in
+// registers and the tile's residual vectors broadcast from shared memory.
+#include "fpc_common.cuh"
+#include "fpc_math.cuh"
+#include "fpc_vq.cuh"
+#include "fpc_vq_search.cuh"
+#include "fpc_encode.cuh"
+
+namespace fpc {
+
+constexpr int kStages = 8;             // weight ring depth
+constexpr int kThreads = kComputeThreads + 128;   // 2 compute warpgroups + 1 producer warpgroup
+constexpr int kLd1 = kH1 + 4;          // 388: padded row strides (floats) -> conflict-free float4 rows
+constexpr int kLd2 = kH2 + 4;          // 132
+constexpr int kLdX = 24;               // input frame row (20 used)
+constexpr int kLdFc = kH2 + 1;         // 129
+
+template <int TU> struct Smem {
+    static constexpr int MT = 4 * TU;
+    static constexpr int kStateSet = MT * (kLd1 + kLd2);                 // floats: [h1 | h2] of one set
+    static constexpr int offRing = 0;
+    static constexpr int offSetA = offRing + kStages * kGroupBytes;
+    static constexpr int offSetB = offSetA + kStateSet * 4;
+    static constexpr int offXin = offSetB + kStateSet * 4;
+    static constexpr int offBias = offXin + MT * kLdX * 4;
+    static constexpr int offFc = offBias + kBiasFloats * 4;              // 18 x 129 weights + 18 bias
+    static constexpr int offRs = offFc + ((kFc * kLdFc + kFc + 3) / 4) * 16;
+    static constexpr int offRq = offRs + MT * kLdR * 4;                  // quantised residual rows (stride 20)
+    static constexpr int offMisc = offRq + MT * 20 * 4;
+    // misc: m1[MT] m2[MT] (float), idx0/idx1/idx2[MT] (int), listA[MT] listB[MT] (int), counts[4]
+    static constexpr int offBars = offMisc + (7 * MT + 4) * 4;
+    static constexpr int total = ((offBars + 2 * kStages * 8 + 127) / 128) * 128;
+    // VQ scratch aliases the DEAD state set (the one holding the previous frame's h1/h2)
+    static constexpr int kScratchBytes = kStateSet * 4;
+};
+
+// ring pipeline state of a compute thread
+struct Pipe {
+    int s;
+    uint32_t ph;
+    __device__ __forceinline__ void advance()
+    {
+        if (++s == kStages) { s = 0; ph ^= 1u; }
+    }
+};
+
+// ------------------------------------------------------------------------------------------
+// one "part" of a pass: NG groups of 4 k, accumulating into r, z and the third gate (n_i or n_h)
+// ------------------------------------------------------------------------------------------
+template <int TU>
+__device__ __forceinline__ void gemm_part(float (&ar)[TU][2], float (&az)[TU][2], float (&an)[TU][2], int ng,
+                                          const float *__restrict__ arow, int lda, const float4 *__restrict__ ring,
+                                          uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
+{
+    for (int g = 0; g < ng; ++g) {
+        mbar_wait(&full[pp.s], pp.ph);
+        const float4 *sw = ring + pp.s * (kGroupFloats / 4) + ug;
+        float4 w[6];
+#pragma unroll
+        for (int c = 0; c < 6; ++c) w[c] = sw[c * 64];
+#pragma unroll
+        for (int i = 0; i < TU; ++i) {
+            const float4 a = *reinterpret_cast<const float4 *>(arow + (size_t)(4 * i) * lda + 4 * g);
+#pragma unroll
+            for (int e = 0; e < 2; ++e) {
+                float r = ar[i][e], z = az[i][e], n = an[i][e];
+                r = __fmaf_rn(w[0 + e].x, a.x, r); z = __fmaf_rn(w[2 + e].x, a.x, z); n = __fmaf_rn(w[4 + e].x, a.x, n);
+                r = __fmaf_rn(w[0 + e].y, a.y, r); z = __fmaf_rn(w[2 + e].y, a.y, z); n = __fmaf_rn(w[4 + e].y, a.y, n);
+                r = __fmaf_rn(w[0 + e].z, a.z, r); z = __fmaf_rn(w[2 + e].z, a.z, z); n = __fmaf_rn(w[4 + e].z, a.z, n);
+                r = __fmaf_rn(w[0 + e].w, a.w, r); z = __fmaf_rn(w[2 + e].w, a.w, z); n = __fmaf_rn(w[4 + e].w, a.w, n);
+                ar[i][e] = r; az[i][e] = z; an[i][e] = n;
+            }
+        }
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&empty[pp.s]);
+        pp.advance();
+    }
+}
+
+// one pass = 128 hidden units of a GRU: bias init, input part, hidden part, gate epilogue
+template <int TU>
+__device__ __forceinline__ void gru_pass(int ngx, int ngh, const float *__restrict__ xrow, int ldx,
+                                         const float *__restrict__ hrow, int ldh, const float *__restrict__ hold,
+                                         float *__restrict__ hnew, int ldo, const float *__restrict__ bias,
+                                         const float4 *__restrict__ ring, uint64_t *full, uint64_t *empty, Pipe &pp,
+                                         int ug, int lane)
+{
+    float ar[TU][2], az[TU][2], ani[TU][2], anh[TU][2];
+    const float2 br = *reinterpret_cast<const float2 *>(bias + 0 * 128 + 2 * ug);
+    const float2 bz = *reinterpret_cast<const float2 *>(bias + 1 * 128 + 2 * ug);
+    const float2 bi = *reinterpret_cast<const float2 *>(bias + 2 * 128 + 2 * ug);
+    const float2 bh = *reinterpret_cast<const float2 *>(bias + 3 * 128 + 2 * ug);
+#pragma unroll
+    for (int i = 0; i < TU; ++i) {
+        ar[i][0] = br.x; ar[i][1] = br.y;
+        az[i][0] = bz.x; az[i][1] = bz.y;
+        ani[i][0] = bi.x; ani[i][1] = bi.y;
+        anh[i][0] = bh.x; anh[i][1] = bh.y;
+    }
+    gemm_part<TU>(ar, az, ani, ngx, xrow, ldx, ring, full, empty, pp, ug, lane);
+    gemm_part<TU>(ar, az, anh, ngh, hrow, ldh, ring, full, empty, pp, ug, lane);
+#pragma unroll
+    for (int i = 0; i < TU; ++i) {
+        const float2 ho = *reinterpret_cast<const float2 *>(hold + (size_t)(4 * i) * ldo);
+        float2 hn;
+        hn.x = gru_update(ar[i][0], az[i][0], ani[i][0], anh[i][0], ho.x);
+        hn.y = gru_update(ar[i][1], az[i][1], ani[i][1], anh[i][1], ho.y);
+        *reinterpret_cast<float2 *>(hnew + (size_t)(4 * i) * ldo) = hn;
+    }
+}
+
+// ------------------------------------------------------------------------------------------
+// the kernel
+// ------------------------------------------------------------------------------------------
+template <int TU>
+__global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P)
+{
+    using S = Smem<TU>;
+    constexpr int MT = S::MT;
+    constexpr int NE = (MT * 20 + kComputeThreads - 1) / kComputeThreads;   // frame elements per thread
+    extern __shared__ __align__(128) unsigned char smem[];
+    float4 *ring = reinterpret_cast<float4 *>(smem + S::offRing);
+    float *setA = reinterpret_cast<float *>(smem + S::offSetA);
+    float *setB = reinterpret_cast<float *>(smem + S::offSetB);
+    float *xin = reinterpret_cast<float *>(smem + S::offXin);
+    float *bias = reinterpret_cast<float *>(smem + S::offBias);
+    float *wfc = reinterpret_cast<float *>(smem + S::offFc);
+    float *bfc = wfc + kFc * kLdFc;
+    float *rs = reinterpret_cast<float *>(smem + S::offRs);
+    float *rq = reinterpret_cast<float *>(smem + S::offRq);
+    float *m1s = reinterpret_cast<float *>(smem + S::offMisc);
+    float *m2s = m1s + MT;
+    int *idx0s = reinterpret_cast<int *>(m2s + MT);
+    int *idx1s = idx0s + MT;
+    int *idx2s = idx1s + MT;
+    int *listA = idx2s + MT;
+    int *listB = listA + MT;
+    int *counts = listB + MT;
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::offBars);
+    uint64_t *empty = full + kStages;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kStages; ++s) {
+            mbar_init(&full[s], 1);
+            mbar_init(&empty[s], kComputeThreads / 32);
+        }
+        mbar_fence_init();
+    }
+    __syncthreads();
+
+    // ---------------- producer warpgroup (only one lane works; it hands its registers over) ----------------
+    if (warp >= kComputeThreads / 32) {
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
+        if (warp == kComputeThreads / 32 && lane == 0) {
+            const long long total = (long long)my_tiles * P.L * kGroupsPerFrame;
+            const char *src = reinterpret_cast<const char *>(P.wstream);
+            int s = 0, gf = 0;
+            uint32_t wraps = 0;
+            for (long long g = 0; g < total; ++g) {
+                if (wraps > 0) mbar_wait(&empty[s], (wraps - 1) & 1u);
+                mbar_arrive_expect_tx(&full[s], kGroupBytes);
+                bulk_g2s(smem + S::offRing + s * kGroupBytes, src + (size_t)gf * kGroupBytes, kGroupBytes, &full[s]);
+                if (++gf == kGroupsPerFrame) gf = 0;
+                if (++s == kStages) { s = 0; ++wraps; }
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
+    const int tg = lane >> 3;
+    const int ug = warp * 8 + (lane & 7);
+    const PackedCodebooks *cbh = reinterpret_cast<const PackedCodebooks *>(P.cb);
+
+    // constants resident for the whole kernel
+    {
+        const float *tail = P.wstream + kStreamFloats;
+        for (int i = tid; i < kBiasFloats; i += kComputeThreads) bias[i] = tail[i];
+        for (int i = tid; i < kFcFloats; i += kComputeThreads) wfc[(i >> 7) * kLdFc + (i & 127)] = tail[kBiasFloats + i];
+        if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
+    }
+    Pipe pp{0, 0u};
+
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int b0 = tile * MT;
+        float *cur = setA, *nxt = setB;
+        for (int i = tid; i < S::kStateSet; i += kComputeThreads) cur[i] = 0.0f;   // h1 = h2 = None -> zeros
+        for (int i = tid; i < MT * kLdX; i += kComputeThreads) xin[i] = 0.0f;      // frame 0 input is all zero
+        for (int i = tid; i < MT * kLdR; i += kComputeThreads) rs[i] = 0.0f;
+        named_bar_sync(1, kComputeThreads);
+
+        for (int fr = 0; fr < P.L; ++fr) {
+            // element ownership for this frame: e = tid + 256 q -> (row u, feature j)
+            float featv[NE], fov[NE], rsv[NE];
+#pragma unroll
+            for (int q = 0; q < NE; ++q) {
+                const int e = tid + kComputeThreads * q;
+                const int u = e / 20, j = e - u * 20;
+                featv[q] = 0.0f; fov[q] = 0.0f; rsv[q] = 0.0f;
+                if (e < MT * 20 && b0 + u < P.B) {
+                    const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                    if (P.mode != kModeDecode) featv[q] = __ldg(P.feat + fo * 20 + j);
+                    else featv[q] = j < kFc ? __ldg(P.rq_in + fo * kFc + j) : __ldg(P.pitch_in + fo * 2 + (j - kFc));
+                }
+            }
+            float *h1c = cur, *h2c = cur + MT * kLd1;
+            float *h1n = nxt, *h2n = nxt + MT * kLd1;
+
+            // ---- GRU 1: three passes of 128 hidden units (wavernn.py:71) ----
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                gru_pass<TU>(kG1x, kG1h, xin + tg * kLdX, kLdX, h1c + tg * kLd1, kLd1,
+                             h1c + tg * kLd1 + pass * 128 + 2 * ug, h1n + tg * kLd1 + pass * 128 + 2 * ug, kLd1,
+                             bias + pass * 512, ring, full, empty, pp, ug, lane);
+            }
+            named_bar_sync(1, kComputeThreads);
+            // ---- GRU 2 (wavernn.py:76): input is the new h1 ----
+            gru_pass<TU>(kG2x, kG2h, h1n + tg * kLd1, kLd1, h2c + tg * kLd2, kLd2, h2c + tg * kLd2 + 2 * ug,
+                         h2n + tg * kLd2 + 2 * ug, kLd2, bias + 3 * 512, ring, full, empty, pp, ug, lane);
+            named_bar_sync(1, kComputeThreads);
+
+            // ---- relu, dual_fc, 2*tanh (wavernn.py:87-92); residual (:196) ----
+#pragma unroll
+            for (int q = 0; q < NE; ++q) {
+                const int e = tid + kComputeThreads * q;
+                const int u = e / 20, j = e - u * 20;
+                if (e < MT * 20 && j < kFc) {
+                    float a = bfc[j];
+                    const float *wr = wfc + j * kLdFc;
+                    const float *hv = h2n + u * kLd2;
+#pragma unroll 8
+                    for (int k = 0; k < kH2; ++k) a = __fmaf_rn(wr[k], fmaxf(hv[k], 0.0f), a);
+                    const float f = __fmul_rn(2.0f, tanh_c(a));
+                    fov[q] = f;
+                    if (P.mode != kModeDecode) {
+                        rsv[q] = __fsub_rn(featv[q], f);
+                        rs[u * kLdR + 3 + j] = rsv[q];
+                    }
+                }
+            }
+            if (P.mode != kModeDecode) {
+                for (int i = tid; i < MT * 20; i += kComputeThreads) rq[i] = 0.0f;
+                named_bar_sync(1, kComputeThreads);
+
+                // ---- indicators (:201-212) and the scalar quantiser for c0 (:217-225) ----
+                for (int u = warp; u < MT; u += 8) {
+                    const bool valid = b0 + u < P.B;
+                    float m1 = 0.0f, m2 = 0.0f;
+                    if (lane == 0 && valid) {
+                        if (P.mask == nullptr) {
+                            float s = 0.0f;
+#pragma unroll
+                            for (int j = 1; j < kFc; ++j) s = __fadd_rn(s, fabsf(rs[u * kLdR + 3 + j]));
+                            m1 = fabsf(rs[u * kLdR + 3]) > P.l1 ? 1.0f : 0.0f;
+                            m2 = s > P.l2 ? 1.0f : 0.0f;
+                        } else {
+                            const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                            m1 = __ldg(P.mask + fo * 2);
+                            m2 = __ldg(P.mask + fo * 2 + 1);
+                        }
+                    }
+                    m1 = __shfl_sync(0xffffffffu, m1, 0);
+                    m2 = __shfl_sync(0xffffffffu, m2, 0);
+                    int i0 = -1;
+                    if (P.mode == kModeQuantize && valid) {
+                        const PackedScl &sb = (m1 != 0.0f) ? cbh->scl : cbh->blscl;
+                        if (sb.n > 0) {
+                            const float x0 = rs[u * kLdR + 3];
+                            float qv;
+                            if (sb.dtype == FPC_F32) {
+                                float q;
+                                i0 = warp_scl_nearest<float>(reinterpret_cast<const float *>(P.cb + sb.off), sb.n, x0, lane, q);
+                                qv = q;
+                            } else {
+                                double q;
+                                i0 = warp_scl_nearest<double>(reinterpret_cast<const double *>(P.cb + sb.off), sb.n, x0, lane, q);
+                                qv = (float)q;
+                            }
+                            if (lane == 0) rq[u * 20] = qv;
+                        }
+                    }
+                    if (lane == 0) { m1s[u] = m1; m2s[u] = m2; idx0s[u] = i0; idx1s[u] = -1; idx2s[u] = -1; }
+                }
+                named_bar_sync(1, kComputeThreads);
+
+                if (P.mode == kModeQuantize) {
+                    // ---- VQ for c1..c17 (:228-240): compact the tile rows by branch ----
+                    if (warp == 0) {
+                        const bool valid = lane < MT && b0 + lane < P.B;
+                        const bool above = valid && m2s[lane < MT ? lane : 0] != 0.0f;
+                        const bool below = valid && !above && cbh->bl.stages > 0;
+                        const unsigned ba = __ballot_sync(0xffffffffu, above);
+                        const unsigned bb = __ballot_sync(0xffffffffu, below);
+                        const unsigned lt = (1u << lane) - 1u;
+                        if (above) listA[__popc(ba & lt)] = lane;
+                        if (below) listB[__popc(bb & lt)] = lane;
+                        if (lane == 0) { counts[0] = __popc(ba); counts[1] = __popc(bb); }
+                    }
+                    named_bar_sync(1, kComputeThreads);
+                    const int nA = counts[0], nB = counts[1];
+                    char *scratch = reinterpret_cast<char *>(cur);   // dead state set (see Smem)
+                    if (nA > 0) vq_dispatch(cbh->vq, P.cb, listA, nA, MT, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                    if (nB > 0) vq_dispatch(cbh->bl, P.cb, listB, nB, MT, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                }
+            } else {
+                named_bar_sync(1, kComputeThreads);
+            }
+
+            // ---- feedback (:242 / :252), outputs, next input frame ----
+#pragma unroll
+            for (int q = 0; q < NE; ++q) {
+                const int e = tid + kComputeThreads * q;
+                const int u = e / 20, j = e - u * 20;
+                if (e < MT * 20) {
+                    const bool valid = b0 + u < P.B;
+                    const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                    float cin;
+                    if (j < kFc) {
+                        float ro, rqo, ruo;
+                        if (P.mode == kModeQuantize) {
+                            rqo = rq[u * 20 + j];
+                            ro = rsv[q];
+                            ruo = 0.0f;
+                            cin = __fadd_rn(fov[q], rqo);
+                        } else if (P.mode == kModeResidual) {
+                            const float m = j == 0 ? m1s[u] : m2s[u];
+                            ruo = __fmul_rn(rsv[q], __fsub_rn(1.0f, m));
+                            ro = __fmul_rn(rsv[q], m);
+                            rqo = 0.0f;
+                            cin = __fadd_rn(fov[q], ro);
+                        } else {
+                            ro = rqo = ruo = 0.0f;
+                            cin = __fadd_rn(fov[q], featv[q]);   // decode: featv holds r_qtz[t]
+                        }
+                        if (valid && P.mode != kModeDecode) {
+                            P.r[fo * kFc + j] = ro;
+                            P.r_qtz[fo * kFc + j] = rqo;
+                            if (P.r_under) P.r_under[fo * kFc + j] = ruo;
+                        }
+                    } else {
+                        cin = featv[q];   // pitch pass-through (:178)
+                    }
+                    xin[u * kLdX + j] = cin;
+                    if (valid) P.c_in[fo * 20 + j] = cin;
+                }
+            }
+            if (P.mode != kModeDecode && tid < MT && b0 + tid < P.B) {
+                const size_t fo = (size_t)(b0 + tid) * P.L + fr;
+                const float m1 = m1s[tid], m2 = m2s[tid];
+                // the reference fills ind*_mask only in the threshold branch (:204,208)
+                if (P.ind1) P.ind1[fo] = P.mask ? 0.0f : m1;
+                if (P.ind2) P.ind2[fo] = P.mask ? 0.0f : m2;
+                if (P.idx) {
+                    int4 v;
+                    v.x = idx0s[tid]; v.y = idx1s[tid]; v.z = idx2s[tid];
+                    v.w = (m1 != 0.0f ? 1 : 0) | (m2 != 0.0f ? 2 : 0);
+                    *reinterpret_cast<int4 *>(P.idx + fo * 4) = v;
+                }
+            }
+            named_bar_sync(1, kComputeThreads);
+            float *t = cur; cur = nxt; nxt = t;
+        }
+    }
+}
+
+template <int TU>
+static int launch_encode(const EncodeParams &P, int grid, cudaStream_t st)
+{
+    using S = Smem<TU>;
+    static bool configured = false;
+    if (!configured) {
+        FPC_CUDA_TRY(cudaFuncSetAttribute(encode_fp32_kernel<TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total));
+        configured = true;
+    }
+    encode_fp32_kernel<TU><<<grid, kThreads, S::total, st>>>(P);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+static int g_num_sms = 0;
+
+int num_sms()
+{
+    if (g_num_sms == 0) {
+        int dev = 0, n = 0;
+        if (cudaGetDevice(&dev) != cudaSuccess) return 0;
+        if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
+        g_num_sms = n;
+    }
+    return g_num_sms;
+}
+
+// utterances per CTA: the tile height that minimises (waves x per-tile cost)
+static int pick_tu(int B, int sms)
+{
+    const int cand[4] = {4, 6, 7, 8};
+    int best = 4;
+    double best_cost = 1e30;
+    for (int c = 0; c < 4; ++c) {
+        const int mt = 4 * cand[c];
+        const int tiles = (B + mt - 1) / mt;
+        const int waves = (tiles + sms - 1) / sms;
+        const double cost = (double)waves * (mt + 6.0);   // +6: per-frame fixed work (barriers, selection)
+        if (cost < best_cost - 1e-9) { best_cost = cost; best = cand[c]; }
+    }
+    return best;
+}
+
+int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu)
+{
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
+    const int tu = force_tu > 0 ? force_tu : pick_tu(P.B, sms);
+    const int mt = 4 * tu;
+    P.ntiles = (P.B + mt - 1) / mt;
+    const int grid = P.ntiles < sms ? P.ntiles : sms;
+    switch (tu) {
+        case 4: return launch_encode<4>(P, grid, st);
+        case 6: return launch_encode<6>(P, grid, st);
+        case 7: return launch_encode<7>(P, grid, st);
+        case 8: return launch_encode<8>(P, grid, st);
+        default: return FPC_ERR_ARG;
+    }
+}
+
+}  // namespace fpc

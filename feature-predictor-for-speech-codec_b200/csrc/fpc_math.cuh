@@ -1,7 +1,7 @@
 // fpc_math.cuh -- canonical fp32 transcendental functions of the predictor.
 //
 // These are the device-side twins of orc_exp_core / orc_sigmoidf / orc_tanhf in
-// oracle/fpc_oracle.c.  They use only IEEE-754 round-to-nearest add / mul / fma / div
+// the CPU restatement (fpc_oracle.c).  They use only IEEE-754 round-to-nearest add / mul / fma / div
 // (explicit intrinsics, never contracted), so the fp32 CUDA path reproduces the oracle bit
 // for bit.  torch's CPU sigmoid/tanh (reference: torch.nn.GRU inside wavernn.py:71,76 and
 // nn.Tanh at :51) differ from these by <= 2 ulp, which is covered by the 1e-4 feature

@@ -1,0 +1,228 @@
+// fpc_pack.cu -- re-tiling of the predictor parameters and codebook files into the images the
+// frame-step kernel streams.  Reference objects: the state_dict of Wavernn
+// (/root/reference/src/models/wavernn.py:37-38,48-52) and the .npy files loaded at
+// quantization/vq_func.py:141,171.
+#include "fpc_common.cuh"
+
+namespace fpc {
+
+thread_local int g_last_cuda_error = 0;
+unsigned long long g_launch_count = 0;
+
+// ------------------------------------------------------------------------------------------
+// fp32 weight stream.  One thread per destination float.
+//   group g of a pass -> [slot c = gate*2 + e][unit pair ug 0..63][kk 0..3]
+//   hidden unit j = pass*128 + 2*ug + e ; k = 4*(group index within part) + kk
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < kStreamFloats) {
+        int g = t / kGroupFloats;
+        int r = t - g * kGroupFloats;
+        int c = r / 256, ug = (r >> 2) & 63, kk = r & 3;
+        int gate = c >> 1, e = c & 1;
+        float v;
+        if (g < 3 * kG1) {
+            int pass = g / kG1, gi = g - pass * kG1;
+            int j = pass * 128 + 2 * ug + e;
+            int row = gate * kH1 + j;
+            if (gi < kG1x) v = w.w_ih1[(size_t)row * kIn + 4 * gi + kk];
+            else v = w.w_hh1[(size_t)row * kH1 + 4 * (gi - kG1x) + kk];
+        } else {
+            int gi = g - 3 * kG1;
+            int j = 2 * ug + e;
+            int row = gate * kH2 + j;
+            if (gi < kG2x) v = w.w_ih2[(size_t)row * kH1 + 4 * gi + kk];
+            else v = w.w_hh2[(size_t)row * kH2 + 4 * (gi - kG2x) + kk];
+        }
+        out[t] = v;
+        return;
+    }
+    t -= kStreamFloats;
+    if (t < kBiasFloats) {
+        // [pass 0..3][kind: br, bz, b_in, b_hn][unit 0..127]; pass 3 is GRU2
+        int pass = t / 512, kind = (t >> 7) & 3, u = t & 127;
+        const float *bi = pass < 3 ? w.b_ih1 : w.b_ih2;
+        const float *bh = pass < 3 ? w.b_hh1 : w.b_hh2;
+        int H = pass < 3 ? kH1 : kH2;
+        int j = pass < 3 ? pass * 128 + u : u;
+        float v;
+        if (kind == 0) v = __fadd_rn(bi[j], bh[j]);
+        else if (kind == 1) v = __fadd_rn(bi[H + j], bh[H + j]);
+        else if (kind == 2) v = bi[2 * H + j];
+        else v = bh[2 * H + j];
+        out[kStreamFloats + t] = v;
+        return;
+    }
+    t -= kBiasFloats;
+    if (t < kFcFloats) {
+        out[kStreamFloats + kBiasFloats + t] = w.w_fc[t];
+        return;
+    }
+    t -= kFcFloats;
+    if (t < kFc) out[kStreamFloats + kBiasFloats + kFcFloats + t] = w.b_fc[t];
+}
+
+// ------------------------------------------------------------------------------------------
+// codebooks: each VQ stage is stored twice, transposed [17][K] for the search (coalesced
+// per-thread codeword loads) and row-major [K][17] for the gathers.
+// ------------------------------------------------------------------------------------------
+template <typename T>
+__global__ void pack_vq_kernel(const T *__restrict__ src, int stages, int K, T *__restrict__ dst_t0,
+                               T *__restrict__ dst_r0, T *__restrict__ dst_t1, T *__restrict__ dst_r1)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    int per = K * kDim;
+    if (t >= stages * per) return;
+    int s = t / per, r = t - s * per;
+    int k = r / kDim, d = r - k * kDim;
+    T v = src[t];
+    T *dt = s == 0 ? dst_t0 : dst_t1;
+    T *dr = s == 0 ? dst_r0 : dst_r1;
+    dt[(size_t)d * K + k] = v;
+    dr[r] = v;
+}
+
+template <typename T>
+__global__ void copy_kernel(const T *__restrict__ src, int n, T *__restrict__ dst)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < n) dst[t] = src[t];
+}
+
+static int check_vq(const void *p, int dtype, int stages, int K, bool required)
+{
+    if (stages == 0) return required ? FPC_ERR_CODEBOOK : FPC_OK;
+    if (!p) return FPC_ERR_ARG;
+    if (dtype != FPC_F32 && dtype != FPC_F64) return FPC_ERR_CODEBOOK;
+    if (stages < 1 || stages > 2) return FPC_ERR_CODEBOOK;       // >2 stages raise in vq_func.py:111
+    if (K < kSurv || K > FPC_MAX_VQ_ENTRIES) return FPC_ERR_CODEBOOK;  // sorted()[:5] needs >= 5 entries
+    return FPC_OK;
+}
+
+static int check_scl(const void *p, int dtype, int n, bool required)
+{
+    if (n == 0) return required ? FPC_ERR_CODEBOOK : FPC_OK;
+    if (!p) return FPC_ERR_ARG;
+    if (dtype != FPC_F32 && dtype != FPC_F64) return FPC_ERR_CODEBOOK;
+    if (n < 1 || n > FPC_MAX_SCL_ENTRIES) return FPC_ERR_CODEBOOK;
+    return FPC_OK;
+}
+
+static int pack_one_vq(const void *src, int dtype, int stages, int K, char *base, size_t &cursor, PackedVq &h,
+                       cudaStream_t st)
+{
+    h.dtype = dtype; h.stages = stages; h.K = K; h.pad = 0;
+    h.off_t[0] = h.off_t[1] = h.off_r[0] = h.off_r[1] = 0;
+    if (stages == 0) return FPC_OK;
+    size_t es = dtype == FPC_F32 ? 4 : 8;
+    size_t one = (((size_t)K * kDim * es) + 255) / 256 * 256;
+    for (int s = 0; s < stages; ++s) {
+        h.off_t[s] = (long long)cursor; cursor += one;
+        h.off_r[s] = (long long)cursor; cursor += one;
+    }
+    int n = stages * K * kDim;
+    int blocks = (n + 255) / 256;
+    if (dtype == FPC_F32)
+        pack_vq_kernel<float><<<blocks, 256, 0, st>>>((const float *)src, stages, K, (float *)(base + h.off_t[0]),
+                                                      (float *)(base + h.off_r[0]), (float *)(base + h.off_t[1]),
+                                                      (float *)(base + h.off_r[1]));
+    else
+        pack_vq_kernel<double><<<blocks, 256, 0, st>>>((const double *)src, stages, K, (double *)(base + h.off_t[0]),
+                                                       (double *)(base + h.off_r[0]), (double *)(base + h.off_t[1]),
+                                                       (double *)(base + h.off_r[1]));
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+static int pack_one_scl(const void *src, int dtype, int n, char *base, size_t &cursor, PackedScl &h, cudaStream_t st)
+{
+    h.dtype = dtype; h.n = n; h.off = 0;
+    if (n == 0) return FPC_OK;
+    h.off = (long long)cursor;
+    cursor += kCbSclMaxBytes;
+    if (dtype == FPC_F32) copy_kernel<float><<<1, 256, 0, st>>>((const float *)src, n, (float *)(base + h.off));
+    else copy_kernel<double><<<1, 256, 0, st>>>((const double *)src, n, (double *)(base + h.off));
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+}  // namespace fpc
+
+using namespace fpc;
+
+extern "C" {
+
+int fpc_version(void) { return FPC_VERSION; }
+
+const char *fpc_status_string(int s)
+{
+    switch (s) {
+        case FPC_OK: return "ok";
+        case FPC_ERR_ARG: return "bad argument (null pointer or negative size)";
+        case FPC_ERR_SHAPE: return "unsupported dimensions";
+        case FPC_ERR_CODEBOOK: return "bad codebook (stages must be 1 or 2, 5..1024 entries, <=256 scalar levels, f32/f64)";
+        case FPC_ERR_WORKSPACE: return "workspace or packed buffer too small";
+        case FPC_ERR_CUDA: return "CUDA runtime error";
+        case FPC_ERR_UNSUPPORTED: return "precision/mode not supported by this build";
+        default: return "unknown status";
+    }
+}
+
+int fpc_last_cuda_error(void) { return g_last_cuda_error; }
+
+unsigned long long fpc_launch_count(void) { return __atomic_load_n(&g_launch_count, __ATOMIC_RELAXED); }
+
+size_t fpc_packed_codebooks_bytes(void) { return kPackedCbBytes; }
+
+int fpc_pack_codebooks(const fpc_codebooks *cb, void *d_packed, size_t packed_bytes, void *stream)
+{
+    if (!cb || !d_packed) return FPC_ERR_ARG;
+    if (packed_bytes < kPackedCbBytes) return FPC_ERR_WORKSPACE;
+    int rc;
+    if ((rc = check_vq(cb->vq, cb->vq_dtype, cb->vq_stages, cb->vq_entries, false))) return rc;
+    if ((rc = check_vq(cb->bl_vq, cb->bl_vq_dtype, cb->bl_vq_stages, cb->bl_vq_entries, false))) return rc;
+    if ((rc = check_scl(cb->scl, cb->scl_dtype, cb->scl_entries, false))) return rc;
+    if ((rc = check_scl(cb->bl_scl, cb->bl_scl_dtype, cb->bl_scl_entries, false))) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    PackedCodebooks h;
+    size_t cursor = kCbHeaderBytes;
+    char *base = (char *)d_packed;
+    if ((rc = pack_one_vq(cb->vq, cb->vq_dtype, cb->vq_stages, cb->vq_entries, base, cursor, h.vq, st))) return rc;
+    cursor = kCbHeaderBytes + kCbVqMaxBytes;
+    if ((rc = pack_one_vq(cb->bl_vq, cb->bl_vq_dtype, cb->bl_vq_stages, cb->bl_vq_entries, base, cursor, h.bl, st)))
+        return rc;
+    cursor = kCbHeaderBytes + 2 * kCbVqMaxBytes;
+    if ((rc = pack_one_scl(cb->scl, cb->scl_dtype, cb->scl_entries, base, cursor, h.scl, st))) return rc;
+    if ((rc = pack_one_scl(cb->bl_scl, cb->bl_scl_dtype, cb->bl_scl_entries, base, cursor, h.blscl, st))) return rc;
+    // The header is tiny and the source is a host stack object: a synchronous copy is the
+    // safe choice (cudaMemcpyAsync from pageable memory stages it before returning anyway).
+    FPC_CUDA_TRY(cudaMemcpyAsync(d_packed, &h, sizeof(h), cudaMemcpyHostToDevice, st));
+    return FPC_OK;
+}
+
+size_t fpc_packed_weights_bytes(int precision)
+{
+    if (precision == FPC_PREC_FP32) return (size_t)kPackedF32Floats * 4;
+    return 0;
+}
+
+int fpc_pack_weights(const fpc_weights *w, int precision, void *d_packed, size_t packed_bytes, void *stream)
+{
+    if (!w || !d_packed) return FPC_ERR_ARG;
+    if (!w->w_ih1 || !w->w_hh1 || !w->b_ih1 || !w->b_hh1 || !w->w_ih2 || !w->w_hh2 || !w->b_ih2 || !w->b_hh2 ||
+        !w->w_fc || !w->b_fc)
+        return FPC_ERR_ARG;
+    cudaStream_t st = (cudaStream_t)stream;
+    if (precision == FPC_PREC_FP32) {
+        if (packed_bytes < (size_t)kPackedF32Floats * 4) return FPC_ERR_WORKSPACE;
+        int n = kStreamFloats + kBiasFloats + kFcFloats + kFc;
+        pack_weights_f32_kernel<<<(n + 255) / 256, 256, 0, st>>>(*w, (float *)d_packed);
+        FPC_LAUNCH_CHECK();
+        return FPC_OK;
+    }
+    return FPC_ERR_UNSUPPORTED;
+}
+
+}  // extern "C"

@@ -1,0 +1,92 @@
+// fpc_vq.cuh -- device-side quantiser arithmetic shared by the fused frame-step kernel and the
+// stand-alone quantiser kernels.
+//
+// Reference: /root/reference/src/quantization/vq_func.py:10-24 (vq_quantize_mbest),
+// :82-131 (quantize_mstage), :167-185 (scl_quantize).  numpy evaluates
+// np.sum((x - cb) ** 2, -1) as t = x - c, e = t * t (each rounded, no fma) followed by its
+// pairwise reduction over the contiguous axis: for 17 terms, eight interleaved partial sums
+// r[j] = e[j] + e[8+j], ((r0+r1)+(r2+r3))+((r4+r5)+(r6+r7)), then + e[16].  The functions
+// here perform exactly those roundings, in the codebook's dtype, so codeword indices are
+// bit-identical to the reference's, ties included (lowest index wins: Python's stable
+// sorted() and np.argmin).
+#pragma once
+#include "fpc_common.cuh"
+
+namespace fpc {
+
+template <typename T> struct Rn;
+template <> struct Rn<float> {
+    static __device__ __forceinline__ float add(float a, float b) { return __fadd_rn(a, b); }
+    static __device__ __forceinline__ float sub(float a, float b) { return __fsub_rn(a, b); }
+    static __device__ __forceinline__ float mul(float a, float b) { return __fmul_rn(a, b); }
+    static __device__ __forceinline__ float inf() { return __int_as_float(0x7f800000); }
+};
+template <> struct Rn<double> {
+    static __device__ __forceinline__ double add(double a, double b) { return __dadd_rn(a, b); }
+    static __device__ __forceinline__ double sub(double a, double b) { return __dsub_rn(a, b); }
+    static __device__ __forceinline__ double mul(double a, double b) { return __dmul_rn(a, b); }
+    static __device__ __forceinline__ double inf() { return __longlong_as_double(0x7ff0000000000000LL); }
+};
+
+// squared distance of x to codeword c over the 17 code dimensions, numpy order
+template <typename T>
+__device__ __forceinline__ T dist17(const T (&x)[kDim], const T (&c)[kDim])
+{
+    T e[kDim];
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) {
+        T t = Rn<T>::sub(x[d], c[d]);
+        e[d] = Rn<T>::mul(t, t);
+    }
+    T r[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) r[j] = Rn<T>::add(e[j], e[8 + j]);
+    T res = Rn<T>::add(Rn<T>::add(Rn<T>::add(r[0], r[1]), Rn<T>::add(r[2], r[3])),
+                       Rn<T>::add(Rn<T>::add(r[4], r[5]), Rn<T>::add(r[6], r[7])));
+    return Rn<T>::add(res, e[16]);
+}
+
+// lexicographic (distance, index) minimum across the warp; every lane gets the result
+template <typename T>
+__device__ __forceinline__ void warp_argmin(T &d, int &i)
+{
+#pragma unroll
+    for (int off = 16; off > 0; off >>= 1) {
+        T od = __shfl_xor_sync(0xffffffffu, d, off);
+        int oi = __shfl_xor_sync(0xffffffffu, i, off);
+        if (od < d || (od == d && oi < i)) { d = od; i = oi; }
+    }
+}
+
+// fp32 fast path of the same reduction: distances are non-negative, so their bit patterns
+// order like unsigned integers and two REDUX.MIN instructions replace the shuffle tree.
+__device__ __forceinline__ void warp_argmin(float &d, int &i, int /*tag*/)
+{
+    unsigned db = __float_as_uint(d);
+    unsigned m = __reduce_min_sync(0xffffffffu, db);
+    unsigned cand = db == m ? (unsigned)i : 0xffffffffu;
+    unsigned w = __reduce_min_sync(0xffffffffu, cand);
+    d = __uint_as_float(m);
+    i = (int)w;
+}
+
+// scalar quantiser for one value by one warp (vq_func.py:175-176): argmin over n codes of
+// (x - code)^2, first minimum.  codes in global memory (n <= 256).
+template <typename T>
+__device__ __forceinline__ int warp_scl_nearest(const T *__restrict__ codes, int n, float x, int lane, T &q)
+{
+    T best = Rn<T>::inf();
+    int bi = 0x7fffffff;
+    T xv = (T)x;
+    for (int k = lane; k < n; k += 32) {
+        T t = Rn<T>::sub(xv, codes[k]);
+        T d = Rn<T>::mul(t, t);
+        if (d < best || bi == 0x7fffffff) { best = d; bi = k; }  // ascending k per lane: first min kept
+    }
+    warp_argmin(best, bi);
+    if (bi == 0x7fffffff) bi = 0;
+    q = codes[bi];
+    return bi;
+}
+
+}  // namespace fpc

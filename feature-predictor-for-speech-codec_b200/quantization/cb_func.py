@@ -1,0 +1,156 @@
+"""Drop-in for /root/reference/src/quantization/cb_func.py (k-means / LBG codebook learning).
+
+    vq_train(data, codebook, nb_entries)   :28-54    grow-by-one LBG + Lloyd
+    find_nearest(data, codebook)           :56-68    float64 direct-form argmin (first minimum)
+    update(data, codebook, nb_entries_tmp) :71-100   one Lloyd iteration (= BASELINE's "k-means iter")
+    quantize(codebook, data)               :103-112  nearest-centroid gather
+
+`data` may be a NumPy array (copied to the device once per call) or a CUDA float32 tensor
+(N,17) that stays resident -- vq_train / train_cb.py call `update` thousands of times on the
+same residuals, so callers that care pass the tensor.  Codebooks are float64 NumPy arrays like
+the reference's.
+
+Several GPUs: when torch.distributed is initialised (one process per GPU), `data` is THIS
+rank's shard of the residual vectors; per-centroid float64 sums and counts are all-reduced
+(NCCL over NVLink) between the assign kernel and the divide, so every rank ends an iteration
+with the same codebook.  The jitter of vq_train comes from NumPy's global RNG exactly as in the
+reference (:41); with several ranks rank 0's draw is broadcast.
+"""
+import numpy as np
+
+import fpc_dist
+import fpc_native as N
+
+
+def _torch():
+    import torch
+    return torch
+
+
+def _data_on_device(data):
+    torch = _torch()
+    N.require_cuda()
+    if isinstance(data, torch.Tensor):
+        t = data.detach()
+        if not t.is_cuda:
+            t = t.cuda()
+        t = t.to(torch.float32)
+    else:
+        t = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=np.float32)).cuda()
+    if t.dim() != 2 or t.shape[1] != 17:
+        raise ValueError("data must be (nb_vectors, 17), got %r" % (tuple(t.shape),))
+    return t.contiguous()
+
+
+def _cb_on_device(codebook, dev):
+    torch = _torch()
+    cb = np.ascontiguousarray(np.asarray(codebook), dtype=np.float64)
+    if cb.ndim != 2 or cb.shape[1] != 17:
+        raise ValueError("codebook must be (nb_entries, 17), got %r" % (cb.shape,))
+    return torch.from_numpy(cb).to(dev)
+
+
+def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
+    """One pass of fpc_kmeans_assign_accumulate over a device shard.
+    Returns (sums (K,17) f64, counts (K,) f64, idx (N,) int32 or None), all on the device."""
+    torch = _torch()
+    dev = data_dev.device
+    K = cb_dev.shape[0]
+    n = data_dev.shape[0]
+    sums = torch.zeros((K, 17), dtype=torch.float64, device=dev) if want_sums else None
+    counts = torch.zeros((K,), dtype=torch.float64, device=dev) if want_sums else None
+    idx = torch.empty((n,), dtype=torch.int32, device=dev) if want_idx else None
+    with torch.cuda.device(dev):
+        N.check(N.lib().fpc_kmeans_assign_accumulate(
+            data_dev.data_ptr(), n, cb_dev.data_ptr(), K,
+            sums.data_ptr() if want_sums else None, counts.data_ptr() if want_sums else None,
+            idx.data_ptr() if want_idx else None, None, 0, N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
+    return sums, counts, idx
+
+
+def update_device(data_dev, cb_dev, group=None):
+    """One Lloyd iteration entirely on the device (+ the all-reduce when distributed).
+    Returns (new codebook (K,17) f64 device tensor, stats (4,) f64 device tensor,
+    global vector count)."""
+    torch = _torch()
+    dev = data_dev.device
+    K = cb_dev.shape[0]
+    sums, counts, _ = assign_accumulate(data_dev, cb_dev)
+    n_total = fpc_dist.allreduce_kmeans(sums, counts, data_dev.shape[0], group)
+    out = torch.empty((K, 17), dtype=torch.float64, device=dev)
+    stats = torch.empty((4,), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        N.check(N.lib().fpc_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), K, float(n_total), out.data_ptr(),
+                                            stats.data_ptr(), N.current_stream(dev)), "fpc_kmeans_finalize")
+    return out, stats, n_total
+
+
+def find_nearest(data, codebook):
+    """cb_func.py:56-68 -> (nb_vectors,) int64 (a CUDA tensor if `data` was one)."""
+    torch = _torch()
+    d = _data_on_device(data)
+    cb = _cb_on_device(codebook, d.device)
+    _, _, idx = assign_accumulate(d, cb, want_idx=True, want_sums=False)
+    if isinstance(data, torch.Tensor):
+        return idx.long()
+    return idx.cpu().numpy().astype(np.int64)
+
+
+def update(data, codebook, nb_entries_tmp, group=None, verbose=True):
+    """cb_func.py:71-100.  Prints the same statistics line as the reference (:96-97)."""
+    d = _data_on_device(data)
+    cb = _cb_on_device(np.asarray(codebook)[:nb_entries_tmp], d.device)
+    out, stats, _ = update_device(d, cb, group)
+    s = stats.cpu().numpy()
+    if verbose and fpc_dist.rank(group) == 0:
+        print('{} - min: {}, max: {}, small: {}, error: {}'.format(
+            nb_entries_tmp, np.array([s[0]]), np.array([s[1]]), np.array([int(s[2])]), s[3]))
+    return out.cpu().numpy()
+
+
+def quantize(codebook, data):
+    """cb_func.py:103-112 -> (nb_vectors, 17) float64."""
+    torch = _torch()
+    d = _data_on_device(data)
+    cb = _cb_on_device(codebook, d.device)
+    _, _, idx = assign_accumulate(d, cb, want_idx=True, want_sums=False)
+    q = torch.empty((d.shape[0], 17), dtype=torch.float64, device=d.device)
+    with torch.cuda.device(d.device):
+        N.check(N.lib().fpc_kmeans_gather(cb.data_ptr(), cb.shape[0], idx.data_ptr(), d.shape[0], q.data_ptr(),
+                                          N.current_stream(d.device)), "fpc_kmeans_gather")
+    if isinstance(data, torch.Tensor):
+        return q
+    return q.cpu().numpy()
+
+
+def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
+    """cb_func.py:28-54.  The residuals go to the device once; each of the 4(K-1)+10 Lloyd
+    iterations is one assign kernel, one (optional) all-reduce and one finalize kernel, with the
+    codebook staying on the device between iterations of a growth step."""
+    torch = _torch()
+    d = _data_on_device(data)
+    dev = d.device
+    ndims = d.shape[1]
+    codebook = np.array(codebook, dtype=np.float64, copy=True)
+    draw = (rng.rand if rng is not None else np.random.rand)
+    # codebook[0] = np.mean(data, 0)  (:33): float64 mean of the (global) data
+    col_sum = d.to(torch.float64).sum(0)
+    n_total = fpc_dist.allreduce_kmeans(col_sum, None, d.shape[0], group)
+    codebook[0] = (col_sum / float(n_total)).cpu().numpy()
+    e = 1
+    while e < nb_entries:
+        codebook[e, :] = codebook[0, :]
+        delta = fpc_dist.broadcast_array(.001 * (draw(e, ndims) / 2), group)
+        codebook[:e, :] += delta
+        e += 1
+        cb = torch.from_numpy(np.ascontiguousarray(codebook[:e])).to(dev)
+        for _ in range(4):
+            cb, stats, _ = update_device(d, cb, group)
+        codebook[:e, :] = cb.cpu().numpy()
+        if verbose and fpc_dist.rank(group) == 0:
+            s = stats.cpu().numpy()
+            print('{} - min: {}, max: {}, small: {}, error: {}'.format(e, s[0], s[1], int(s[2]), s[3]))
+    cb = torch.from_numpy(np.ascontiguousarray(codebook[:nb_entries])).to(dev)
+    for _ in range(10):
+        cb, stats, _ = update_device(d, cb, group)
+    return cb.cpu().numpy()

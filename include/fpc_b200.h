@@ -12,7 +12,7 @@
  *   fpc_decode                 <- models/wavernn.py:367-379   Wavernn.decoder (receiver replay)
  *   fpc_pack_weights           <- models/wavernn.py:37-38,48-52  parameters of rnn1/rnn2/dual_fc
  *   fpc_pack_codebooks         <- quantization/vq_func.py:141,171  the np.load of the four files
- *   fpc_vq_quantize            <- quantization/vq_func.py:134-164  vq_quantize / quantize_mstage
+ *   fpc_vq_quantize_packed     <- quantization/vq_func.py:134-164  vq_quantize / quantize_mstage
  *   fpc_scl_quantize           <- quantization/vq_func.py:167-185  scl_quantize
  *   fpc_index_histogram        <- models/wavernn.py:189,221-240    cb_tot accumulation
  *   fpc_kmeans_assign_accumulate <- quantization/cb_func.py:56-68,82-86  find_nearest + sums
@@ -37,6 +37,10 @@
 
 #ifdef __cplusplus
 extern "C" {
+#endif
+/* the library is built with -fvisibility=hidden; exactly the declarations below are exported */
+#if defined(__GNUC__)
+#pragma GCC visibility push(default)
 #endif
 
 #define FPC_VERSION 100 /* 0.1.0 */
@@ -164,10 +168,14 @@ int fpc_index_histogram(const int32_t *d_idx, long n_frames, unsigned long long 
 /* ---------------------------------------------------------------------------------------------
  * stand-alone quantisers  (vq_func.py:134-185)
  * ------------------------------------------------------------------------------------------- */
-/* d_x (n,17) float32; d_cb (stages,K,17) of `dtype`; d_q (n,17) of `dtype` (numpy returns the
- * codebook dtype); d_idx (n,stages) int32. */
-int fpc_vq_quantize(const float *d_x, long n, const void *d_cb, int dtype, int stages, int entries,
-                    void *d_q, int32_t *d_idx, void *stream);
+/* vq_quantize on a codebook file that fpc_pack_codebooks has already placed in a packed image
+ * (the host mirror caches one image per file, where the reference re-reads the .npy on every
+ * call, vq_func.py:141).  which: 0 = the cfg['cb_path'] slot of the image, 1 = the
+ * cfg['bl_cb_path'] slot.  dtype / stages must equal what the slot was packed with.
+ * d_x (n,17) float32; d_q (n,17) of `dtype` (numpy returns the codebook dtype, vq_func.py:161-164);
+ * d_idx (n,stages) int32. */
+int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebooks, int which, int dtype,
+                           int stages, void *d_q, int32_t *d_idx, void *stream);
 /* d_x (n) float32; d_codes (n_code) of `dtype`; d_q (n) of `dtype`; d_idx (n) int32 */
 int fpc_scl_quantize(const float *d_x, long n, const void *d_codes, int dtype, int n_code, void *d_q,
                      int32_t *d_idx, void *stream);
@@ -189,6 +197,9 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 
+#if defined(__GNUC__)
+#pragma GCC visibility pop
+#endif
 #ifdef __cplusplus
 }
 #endif

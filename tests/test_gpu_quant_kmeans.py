@@ -1,0 +1,133 @@
+"""GPU parity tests of the stand-alone quantisers (quantization/vq_func.py) and the k-means
+codebook learner (quantization/cb_func.py) against the reference's golden vectors and the oracle.
+
+Bars: codeword / centroid indices bit-exact (integer work); quantised values bit-exact (they are
+gathered codewords); k-means centroids within 1e-12 relative of the reference (float64 sums are
+accumulated in a different order than the reference's data-order Python loop)."""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import load_golden
+
+pytestmark = pytest.mark.gpu
+CENTROID_RTOL = 1e-12
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device; the fpc_b200 path has no CPU fallback")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def tmpd():
+    with tempfile.TemporaryDirectory(prefix="fpc_q_") as d:
+        yield d
+
+
+@pytest.mark.parametrize("tag", ["f32", "f64"])
+def test_quantizers_vs_reference_golden(torch_cuda, tmpd, tag):
+    from quantization import vq_func
+    g = load_golden("quantizers")
+    p2, p1, ps = (os.path.join(tmpd, "%s_%s.npy" % (n, tag)) for n in ("cb2", "cb1", "scl"))
+    np.save(p2, g["cb2_" + tag]); np.save(p1, g["cb1_" + tag]); np.save(ps, g["scl_" + tag])
+    x, xs = g["x_" + tag], g["xs_" + tag]
+    q2, tot2 = vq_func.vq_quantize(x, p2)
+    assert q2.dtype == g["q2b_" + tag].dtype and np.array_equal(q2, g["q2b_" + tag])
+    assert np.array_equal(tot2[0], g["hist2b0_" + tag]) and np.array_equal(tot2[1], g["hist2b1_" + tag])
+    _, i2 = vq_func.vq_quantize_indices(x, p2)
+    assert np.array_equal(i2, g["i2_" + tag])
+    assert i2[0, 0] == 3 and i2[0, 1] == 20           # forced ties -> lowest index
+    q1, i1 = vq_func.vq_quantize_indices(x, p1)
+    assert np.array_equal(i1, g["i1_" + tag]) and np.array_equal(q1, g["q1_" + tag])
+    assert i1[1, 0] == 7
+    # one vector per call, as the encoder of the reference does (wavernn.py:230)
+    for k in (0, 1, 5):
+        q, tot = vq_func.vq_quantize(x[k:k + 1], p2)
+        assert np.array_equal(q[0], g["q2_" + tag][k])
+        assert int(np.argmax(tot[0])) == g["i2_" + tag][k, 0] and int(np.argmax(tot[1])) == g["i2_" + tag][k, 1]
+    qs, tots = vq_func.scl_quantize(xs, ps)
+    assert qs.shape == g["qs_" + tag].shape and np.array_equal(qs, g["qs_" + tag])
+    assert np.array_equal(tots, g["hists_" + tag])
+    # quantize_mstage on arrays
+    cs, ix = vq_func.quantize_mstage(x[3], [64, 64], g["cb2_" + tag])
+    assert np.array_equal(ix, g["i2_" + tag][3]) and np.array_equal(cs, g["q2_" + tag][3])
+
+
+def test_vq_large_batch_vs_oracle(torch_cuda, oracle, synth, tmpd):
+    from quantization import vq_func
+    cbs = synth.make_codebooks(0)
+    for name, key in (("above", "cb_path"), ("below", "bl_cb_path")):
+        for dt in (np.float32, np.float64):
+            p = os.path.join(tmpd, "%s_%s.npy" % (name, np.dtype(dt).name))
+            np.save(p, cbs[key].astype(dt))
+            g = np.random.Generator(np.random.Philox(key=11))
+            x = (g.standard_normal((1000 + 37, 17)) * 0.1).astype(np.float32)
+            q, idx = vq_func.vq_quantize_indices(x, p)
+            qo, io = oracle.vq_quantize(cbs[key].astype(dt), x)
+            assert np.array_equal(idx, io)
+            assert np.array_equal(q, qo.astype(dt))
+    # tensors in -> tensors out (device-resident use)
+    xt = torch_cuda.from_numpy(x).cuda()
+    qt, it = vq_func.vq_quantize_indices(xt, p)
+    assert qt.is_cuda and np.array_equal(it.cpu().numpy(), io)
+
+
+def test_kmeans_vs_reference_golden(torch_cuda, oracle):
+    from quantization import cb_func
+    g = load_golden("kmeans")
+    data = g["data"]
+    idx0 = cb_func.find_nearest(data, g["cb0"])
+    assert idx0.dtype == np.int64 and np.array_equal(idx0, g["idx0"])
+    cb1 = cb_func.update(data, g["cb0"], 64, verbose=False)
+    assert cb1.dtype == np.float64
+    np.testing.assert_allclose(cb1, g["cb1"], rtol=CENTROID_RTOL, atol=1e-300)
+    assert np.all(cb1[60:] == 0.0)                    # empty clusters collapse to the zero vector
+    cb2 = cb_func.update(data, g["cb1"], 64, verbose=False)
+    np.testing.assert_allclose(cb2, g["cb2"], rtol=CENTROID_RTOL, atol=1e-300)
+    q = cb_func.quantize(g["cb2"], data)
+    assert np.array_equal(q, g["q"])
+    # seeded grow-by-one LBG: same jitter stream as the reference's np.random.seed(1234) run
+    np.random.seed(int(g["train_seed"]))
+    cbt = cb_func.vq_train(g["train_data"], np.zeros((8, 17)), 8)
+    np.testing.assert_allclose(cbt, g["train_cb"], rtol=1e-9, atol=1e-12)
+
+
+@pytest.mark.parametrize("N,K", [(1, 1), (31, 1), (5000, 7), (20000, 33), (100003, 512), (60000, 1024)])
+def test_kmeans_assign_vs_oracle(torch_cuda, oracle, synth, N, K):
+    """Indices are bit-exact for every K of the grow-by-one schedule (arbitrary K, not only 1024),
+    including near-ties produced by duplicated centroids and data lying exactly on centroids."""
+    from quantization import cb_func
+    data = synth.make_kmeans_data(N, seed=21, n_components=64)
+    g = np.random.Generator(np.random.Philox(key=22))
+    cb = g.standard_normal((K, 17)) * 0.1
+    if K >= 7:
+        cb[5] = cb[2]                                  # exact duplicate -> ties resolve to index 2
+        cb[6] = data[min(N - 1, 3)].astype(np.float64)  # a centroid sitting exactly on a data point
+        cb[3] = cb[4] * (1 + 2.0 ** -40)               # near-duplicate below fp32 resolution
+    idx = cb_func.find_nearest(data, cb)
+    ref = oracle.find_nearest(data, cb)
+    assert np.array_equal(idx, ref)
+    new = cb_func.update(data, cb, K, verbose=False)
+    want, _, counts, stats = oracle.kmeans_update(data, cb, with_details=True)
+    np.testing.assert_allclose(new, want, rtol=CENTROID_RTOL, atol=1e-300)
+
+
+def test_kmeans_device_resident(torch_cuda, oracle, synth):
+    from quantization import cb_func
+    torch = torch_cuda
+    data = synth.make_kmeans_data(30000, seed=23, n_components=32)
+    d = torch.from_numpy(data).cuda()
+    cb = np.random.Generator(np.random.Philox(key=24)).standard_normal((40, 17)) * 0.1
+    cbd = torch.from_numpy(cb).cuda()
+    for _ in range(3):
+        cbd, stats, n = cb_func.update_device(d, cbd)
+        cb = oracle.kmeans_update(data, cb)
+        np.testing.assert_allclose(cbd.cpu().numpy(), cb, rtol=1e-11, atol=1e-300)
+        cb = cbd.cpu().numpy()      # follow the device trajectory so rounding noise does not compound
+    assert n == 30000

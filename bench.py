@@ -272,6 +272,12 @@ def run_ours(args):
         e2e_ms = e0.elapsed_time(e1)
         checksum = float(host_out["c_in"][0, -1].sum())   # the result really is on the host
 
+    del feat_e2e, host_out
+    kmeans = None
+    if args.workload in ("both", "kmeans"):
+        torch.cuda.empty_cache()
+        kmeans = bench_kmeans(args, torch, dist, dev, rank, world, barrier)
+
     t = torch.tensor([ms_total, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -319,10 +325,100 @@ def run_ours(args):
                 "sample": "%d utterances x %d frames, one pass (%.1f s)" % (n_utts, L, dt),
                 "note": "C restatement of the reference (oracle/), OpenMP over utterances; the Python reference itself "
                         "ran at 12.3 frames/s per process in the build container (BASELINE.md)"}
+        if kmeans is not None:
+            line["kmeans"] = kmeans
         print(json.dumps(line), flush=True)
     if world > 1:
         dist.destroy_process_group()
     tmp.cleanup()
+
+
+
+# ---------------------------------------------------------------------------------------------
+# second metric: k-means iters/s (one iter = one cb_func.update over the whole residual set)
+# ---------------------------------------------------------------------------------------------
+def make_kmeans_shard(torch, dev, n_total, rank, world, chunk=1 << 20):
+    """This rank's shard of the N x 17 synthetic residual set, generated on the device: mixture of
+    2048 Gaussians (centres N(0, 0.1^2) from a Philox seed, spread 0.03).  Chunks of 2^20 vectors are
+    seeded by chunk id, so the global data set does not depend on the number of ranks."""
+    import numpy as np
+    import fpc_dist
+    centres = torch.from_numpy((np.random.Generator(np.random.Philox(key=0)).standard_normal((2048, 17)) * 0.1)
+                               .astype(np.float32)).to(dev)
+    first, cnt = fpc_dist.shard_range(n_total, rank, world)
+    out = torch.empty((cnt, 17), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    pos = first
+    while pos < first + cnt:
+        c = pos // chunk
+        lo, hi = c * chunk, min((c + 1) * chunk, n_total)
+        g.manual_seed(1000003 + c)
+        comp = torch.randint(0, 2048, (hi - lo,), generator=g, device=dev)
+        block = centres[comp] + 0.03 * torch.randn((hi - lo, 17), generator=g, device=dev)
+        a, b = max(lo, first), min(hi, first + cnt)
+        out[a - first:b - first] = block[a - lo:b - lo]
+        pos = hi
+    return out
+
+
+def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
+    import numpy as np
+    import fpc_native
+    from quantization import cb_func
+    n_total = args.kmeans_vectors
+    data = make_kmeans_shard(torch, dev, n_total, rank, world)
+    res = {}
+    for K in (1024, 512):
+        cb0 = np.random.Generator(np.random.Philox(key=7)).standard_normal((K, 17)) * 0.1
+        cb = torch.from_numpy(cb0).to(dev)
+        for _ in range(2):                       # warm-up; also moves centroids off the random init
+            cb, _, _ = cb_func.update_device(data, cb)
+        barrier()
+        stream = torch.cuda.current_stream(dev)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = fpc_native.launch_count()
+        iters = args.kmeans_iters
+        e0.record(stream)
+        for _ in range(iters):
+            cb, stats, n_seen = cb_func.update_device(data, cb)
+        e1.record(stream)
+        barrier()
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / iters
+        flops = 3.0 * n_total * K * 17
+        res["K%d" % K] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "gpu_launches": int(fpc_native.launch_count() - n0),
+                          "fp32_direct_form_tflops": flops / (ms * 1e-3) / 1e12,
+                          "hbm_gbs": n_total * 68.0 / world / (ms * 1e-3) / 1e9,
+                          "empty_clusters": float(stats[2].item()), "vectors_seen": int(n_seen)}
+    res["vectors"] = n_total
+    res["sharding"] = "%d vectors per rank, all-reduce of (K,17) sums + (K) counts per iteration" % data.shape[0]
+    res["scaling"] = "strong"
+    if rank == 0 and world == 1 and not args.no_cpu_baseline:
+        # e2e: the reference-facing call with a HOST array (H2D of the data inside the timed region)
+        nh = min(n_total, 8_000_000)
+        host = data[:nh].cpu().pin_memory()
+        cbh = cb.cpu().numpy()
+        cb_func.update(host, cbh, 512, verbose=False)
+        t0 = time.perf_counter()
+        cb_func.update(host, cbh, 512, verbose=False)
+        dt = time.perf_counter() - t0
+        res["e2e_host_call"] = {"call": "cb_func.update(host array, K=512)", "vectors": nh, "seconds": dt,
+                                "h2d_bytes": nh * 68, "iters_per_s_scaled_to_all_vectors": nh / dt / n_total}
+        sys.path.insert(0, os.path.join(ROOT, "oracle"))
+        import oracle as O
+        ns = 200_000
+        sample = data[:ns].cpu().numpy()
+        t0 = time.perf_counter()
+        O.kmeans_update(sample, cbh)
+        dt = time.perf_counter() - t0
+        res["cpu_baseline"] = {"kind": "port", "cores": O.num_threads(), "sample": "%d vectors, K=512, one update" % ns,
+                               "iters_per_s_scaled_to_all_vectors": ns / dt / n_total,
+                               "note": "reference cb_func.update measured 0.39 iters/s at N=20000, K=1024 (BASELINE.md) "
+                                       "= 1.6e-4 iters/s scaled to 50 M vectors"}
+    del data
+    return res
 
 
 def main():
@@ -335,6 +431,10 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance (10 ms each)")
     ap.add_argument("--thresholds", choices=("readme", "calibrated"), default="readme")
     ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--workload", choices=("both", "encode", "kmeans"), default="both",
+                    help="encode is always the headline line; 'both' appends the k-means iters/s object")
+    ap.add_argument("--kmeans-vectors", type=int, default=50_000_000, help="total residual vectors (all ranks)")
+    ap.add_argument("--kmeans-iters", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":

@@ -197,6 +197,12 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 
+/* ---------------------------------------------------------------------------------------------
+ * self-test of the tensor-core plumbing (tcgen05.mma / TMEM) the bf16 predictor is built on:
+ * d_out (128,N) f32 = A (128,K) bf16 x B (N,K) bf16 ^T.  16 <= N <= 256, N % 16 == 0, K % 16 == 0.
+ * ------------------------------------------------------------------------------------------- */
+int fpc_selftest_umma(const void *d_a_bf16, const void *d_b_bf16, int N, int K, float *d_out, void *stream);
+
 #if defined(__GNUC__)
 #pragma GCC visibility pop
 #endif

@@ -272,7 +272,15 @@ def run_ours(args):
         e2e_ms = e0.elapsed_time(e1)
         checksum = float(host_out["c_in"][0, -1].sum())   # the result really is on the host
 
+    d2h_bytes = int(sum(v.numel() * v.element_size() for v in out.values()))
     del feat_e2e, host_out
+    bf16 = None
+    if args.workload in ("both", "bf16"):
+        del feat_d
+        for k in list(out):
+            out[k] = out[k][:0]
+        torch.cuda.empty_cache()
+        bf16 = bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, l2)
     kmeans = None
     if args.workload in ("both", "kmeans"):
         torch.cuda.empty_cache()
@@ -303,7 +311,7 @@ def run_ours(args):
                        "parallelism": "utterance shards, %d rank(s), no collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(feat_h.numel() * 4),
-                    "d2h_bytes_per_step": int(sum(v.numel() * v.element_size() for v in out.values())),
+                    "d2h_bytes_per_step": d2h_bytes,
                     "checksum": checksum},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
@@ -325,6 +333,8 @@ def run_ours(args):
                 "sample": "%d utterances x %d frames, one pass (%.1f s)" % (n_utts, L, dt),
                 "note": "C restatement of the reference (oracle/), OpenMP over utterances; the Python reference itself "
                         "ran at 12.3 frames/s per process in the build container (BASELINE.md)"}
+        if bf16 is not None:
+            line["bf16"] = bf16
         if kmeans is not None:
             line["kmeans"] = kmeans
         print(json.dumps(line), flush=True)
@@ -421,6 +431,57 @@ def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
     return res
 
 
+# ---------------------------------------------------------------------------------------------
+# bf16 leg (BASELINE.json configs[2]): GRU gate GEMMs on tcgen05 at a 16k-utterance batch per GPU
+# ---------------------------------------------------------------------------------------------
+def bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, l2):
+    import fpc_native
+    U, L = args.bf16_utts, args.frames
+    base = torch.from_numpy(make_inputs(S, rank * U, min(U, 512), L)).to(dev)
+    feat = base.repeat((U + base.shape[0] - 1) // base.shape[0], 1, 1)[:U].contiguous()
+    out = {"c_in": torch.empty((U, L, 20), device=dev), "r": torch.empty((U, L, 18), device=dev),
+           "r_qtz": torch.empty((U, L, 18), device=dev), "ind1": torch.empty((U, L, 1), device=dev),
+           "ind2": torch.empty((U, L, 1), device=dev), "idx": torch.empty((U, L, 4), dtype=torch.int32, device=dev)}
+    prev = model.precision
+    model.precision = fpc_native.FPC_PREC_BF16
+    try:
+        with torch.no_grad():
+            for _ in range(2):
+                res = model.encode_device(cfg, feat, None, l1, l2, qtz=True, want_under=False, out=out)
+            barrier()
+            stream = torch.cuda.current_stream(dev)
+            e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            n0 = fpc_native.launch_count()
+            e0.record(stream)
+            for _ in range(args.bf16_steps):
+                res = model.encode_device(cfg, feat, None, l1, l2, qtz=True, want_under=False, out=out)
+            e1.record(stream)
+            barrier()
+            launches = fpc_native.launch_count() - n0
+            p1, p2 = float(res.ind1.mean().item()), float(res.ind2.mean().item())
+    finally:
+        model.precision = prev
+    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms = float(t.item()) / args.bf16_steps
+    pk, _ = peaks()
+    fq = flops_per_frame(p1, p2) - F_GRU
+    fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
+    per_gpu = U * L / (ms * 1e-3)
+    return {"workload": "closed-loop encode, %d utterances x %d frames per GPU (BASELINE.json configs[2]), bf16 predictor on "
+                        "tcgen05, bf16 recurrent state, exact fp32 quantisers" % (U, L),
+            "value": per_gpu * world, "unit": UNIT, "ms_per_step": ms, "steps": args.bf16_steps, "gpu_launches": int(launches),
+            "above_threshold_fraction": {"c0": p1, "c1_17": p2},
+            "roofline": {"bound": "fp32", "what": "quantiser work (direct-form VQ + scalar) on the FP32 pipe",
+                         "achieved": per_gpu * fq / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
+                         "frac": per_gpu * fq / 1e12 / fp32_peak, "flop_per_frame": fq},
+            "tensor": {"achieved": per_gpu * F_GRU / 1e12, "peak": pk["bf16_tflops_sustained"], "unit": "TFLOP/s",
+                       "frac": per_gpu * F_GRU / 1e12 / pk["bf16_tflops_sustained"], "flop_per_frame": F_GRU},
+            "tolerance": "tests/test_gpu_bf16.py: predictor within 3e-2 abs of the fp32 oracle before the first index "
+                         "divergence; decode(encode(x)) bit-exact; quantisers exact on the residual the kernel saw"}
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
@@ -431,8 +492,10 @@ def main():
     ap.add_argument("--frames", type=int, default=1000, help="frames per utterance (10 ms each)")
     ap.add_argument("--thresholds", choices=("readme", "calibrated"), default="readme")
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--workload", choices=("both", "encode", "kmeans"), default="both",
-                    help="encode is always the headline line; 'both' appends the k-means iters/s object")
+    ap.add_argument("--workload", choices=("both", "encode", "kmeans", "bf16"), default="both",
+                    help="the fp32 encode is always the headline line; 'both' appends the bf16 and k-means objects")
+    ap.add_argument("--bf16-utts", type=int, default=16384)
+    ap.add_argument("--bf16-steps", type=int, default=3)
     ap.add_argument("--kmeans-vectors", type=int, default=50_000_000, help="total residual vectors (all ranks)")
     ap.add_argument("--kmeans-iters", type=int, default=3)
     ap.add_argument("--cpu-seconds", type=float, default=15.0)

@@ -100,7 +100,7 @@ int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, con
     if (io->B == 0 || io->L == 0) return FPC_OK;
     if (!io->d_feat || !io->d_c_in || !io->d_r || !io->d_r_qtz) return FPC_ERR_ARG;
     if (io->qtz && !d_packed_codebooks) return FPC_ERR_ARG;
-    if (precision != FPC_PREC_FP32) return FPC_ERR_UNSUPPORTED;
+    if (precision != FPC_PREC_FP32 && precision != FPC_PREC_BF16) return FPC_ERR_UNSUPPORTED;
     EncodeParams P;
     P.wstream = (const float *)d_packed_weights;
     P.cb = (const char *)d_packed_codebooks;
@@ -114,6 +114,7 @@ int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, con
     P.mode = io->qtz ? kModeQuantize : kModeResidual;
     P.l1 = io->l1; P.l2 = io->l2;
     P.ntiles = 0;
+    if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }
 
@@ -125,7 +126,7 @@ int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *
     if (B < 0 || L < 0) return FPC_ERR_ARG;
     if (B == 0 || L == 0) return FPC_OK;
     if (!d_r_qtz || !d_pitch || !d_c_out) return FPC_ERR_ARG;
-    if (precision != FPC_PREC_FP32) return FPC_ERR_UNSUPPORTED;
+    if (precision != FPC_PREC_FP32 && precision != FPC_PREC_BF16) return FPC_ERR_UNSUPPORTED;
     EncodeParams P;
     P.wstream = (const float *)d_packed_weights;
     P.cb = nullptr; P.feat = nullptr; P.mask = nullptr;
@@ -133,6 +134,7 @@ int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *
     P.c_in = d_c_out; P.r = nullptr; P.r_qtz = nullptr; P.r_under = nullptr;
     P.ind1 = nullptr; P.ind2 = nullptr; P.idx = nullptr;
     P.B = B; P.L = L; P.mode = kModeDecode; P.l1 = 0.0f; P.l2 = 0.0f; P.ntiles = 0;
+    if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }
 

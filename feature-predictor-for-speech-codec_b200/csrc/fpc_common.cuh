@@ -110,9 +110,14 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t *bar, uint32_t parity)
         : "memory");
     return ok != 0;
 }
+// Spin on the phase.  A hand-off that never completes is a protocol bug: after ~8 s the thread traps,
+// so the launch fails with an error instead of hanging the device.
 __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
 {
+    if (mbar_try_wait(bar, parity)) return;
+    const long long t0 = clock64();
     while (!mbar_try_wait(bar, parity)) {
+        if (clock64() - t0 > 16000000000LL) __trap();
     }
 }
 // global -> shared bulk copy, completion counted in bytes on an mbarrier

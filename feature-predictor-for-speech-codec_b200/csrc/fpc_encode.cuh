@@ -21,6 +21,10 @@ struct EncodeParams {
 };
 
 int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu);
+// bf16 tensor-core predictor (fpc_encode_bf16.cu); wstream then points at the bf16 image
+int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu);
+size_t packed_bf16_bytes();
+int pack_weights_bf16(const fpc_weights *w, void *d_packed, cudaStream_t st);
 int num_sms();
 
 }  // namespace fpc

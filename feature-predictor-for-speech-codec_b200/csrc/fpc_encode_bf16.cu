@@ -1,0 +1,579 @@
+// fpc_encode_bf16.cu -- fused persistent closed-loop frame-step kernel, bf16 predictor on the
+// 5th-generation tensor cores (tcgen05.mma, accumulators in TMEM, weights fed by the TMA engine).
+//
+// Same contract as fpc_encode_fp32.cu (Wavernn.encoder, /root/reference/src/models/wavernn.py:165-256)
+// with the GRU gate contractions (:71,76) evaluated as bf16 x bf16 -> fp32 tensor-core products; the
+// thresholds, both quantisers (exact fp32/fp64 arithmetic of quantization/vq_func.py) and the feedback
+// are the same CUDA-core code as in the fp32 kernel.
+//
+// Orientation.  Per CTA a tile of NU (32 or 64) utterances.  The products are computed transposed,
+//     D^T [128 gate rows x NU utterances] += W_tile [128 x 16] * Act [NU x 16]^T
+// so that TMEM lane = hidden unit, TMEM column = utterance: the weight tile is the A operand
+// (M = 128), the activations are the B operand (N = NU), and a pass of 128 hidden units needs
+// 4 * NU accumulator columns (r, z, n_i, n_h).  The recurrent state is kept as bf16 operand tiles in
+// shared memory ([x(32) | h1(384)] ping-pong, h2 in place): what the tensor core reads IS the state.
+//
+// Roles (384 threads): warps 0-7 compute -- gate epilogue straight from TMEM (tcgen05.ld; lane quarter
+// = warp % 4, column half = warp / 4), then FC, residual, thresholds, scalar quantiser, m-best VQ and
+// the feedback; warp 8 lane 0 streams the packed bf16 weight image (1.35 MB per frame, L2 resident)
+// through a 4-stage x 12 KB ring with bulk async copies; warp 9 lane 0 issues the MMAs.  Hand-offs are
+// mbarriers: ring full/empty (TMA tx bytes / tcgen05.commit), accumulator full/empty, activations
+// ready (generic-proxy writes fenced to the async proxy).
+#include "fpc_common.cuh"
+#include "fpc_math.cuh"
+#include "fpc_vq.cuh"
+#include "fpc_vq_search.cuh"
+#include "fpc_encode.cuh"
+#include "fpc_umma.cuh"
+
+namespace fpc {
+
+constexpr int kBStages = 4;
+constexpr int kBTileBytes = 128 * 16 * 2;                      // one A tile: 128 gate rows x K = 16, bf16
+constexpr int kBStageBytes = 3 * kBTileBytes;                  // r, z and the third gate (n_i or n_h)
+constexpr int kBG1Steps = 2 + kH1 / 16;                        // 26: x padded to 32, then h1
+constexpr int kBG2Steps = kH1 / 16 + kH2 / 16;                 // 32: h1' then h2
+constexpr int kBStepsPerFrame = 3 * kBG1Steps + kBG2Steps;     // 110
+constexpr int kBStreamElems = kBStepsPerFrame * 3 * 2048;
+constexpr size_t kBStreamBytes = (size_t)kBStreamElems * 2;    // 1 351 680
+constexpr int kBTailFloats = ((kBiasFloats + kFcFloats + kFc + 3) / 4) * 4;
+constexpr int kXK = 32 + kH1;                                  // K extent of the [x | h1] operand tile
+constexpr int kBThreads = kComputeThreads + 128;
+constexpr int kLdFcB = kH2 + 1;
+
+size_t packed_bf16_bytes() { return kBStreamBytes + (size_t)kBTailFloats * 4; }
+
+// ------------------------------------------------------------------------------------------
+// weight image: [110 steps][3 tiles][2 k-chunks][128 rows][8 k] bf16, then the fp32 tail
+// (biases [4 passes][br+bhr, bz+bhz, b_in, b_hn][128], FC weights, FC bias)
+// ------------------------------------------------------------------------------------------
+__global__ void pack_weights_bf16_kernel(fpc_weights w, unsigned char *__restrict__ out)
+{
+    int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < kBStreamElems) {
+        const int step = t / 6144, r0 = t - step * 6144;
+        const int tile = r0 / 2048, r1 = r0 - tile * 2048;
+        const int chunk = r1 / 1024, r2 = r1 - chunk * 1024;
+        const int row = r2 >> 3, kk = chunk * 8 + (r2 & 7);
+        float v = 0.0f;
+        if (step < 3 * kBG1Steps) {
+            const int pass = step / kBG1Steps, i = step - pass * kBG1Steps;
+            const int grow = tile * kH1 + pass * 128 + row;          // gate row (r, z, n) of rnn1
+            if (i < 2) {
+                const int k = 16 * i + kk;
+                if (k < kIn) v = w.w_ih1[(size_t)grow * kIn + k];
+            } else {
+                v = w.w_hh1[(size_t)grow * kH1 + 16 * (i - 2) + kk];
+            }
+        } else {
+            const int i = step - 3 * kBG1Steps;
+            const int grow = tile * kH2 + row;
+            if (i < kH1 / 16) v = w.w_ih2[(size_t)grow * kH1 + 16 * i + kk];
+            else v = w.w_hh2[(size_t)grow * kH2 + 16 * (i - kH1 / 16) + kk];
+        }
+        reinterpret_cast<__nv_bfloat16 *>(out)[t] = __float2bfloat16_rn(v);
+        return;
+    }
+    t -= kBStreamElems;
+    float *tail = reinterpret_cast<float *>(out + kBStreamBytes);
+    if (t < kBiasFloats) {
+        const int pass = t / 512, kind = (t >> 7) & 3, u = t & 127;
+        const float *bi = pass < 3 ? w.b_ih1 : w.b_ih2;
+        const float *bh = pass < 3 ? w.b_hh1 : w.b_hh2;
+        const int H = pass < 3 ? kH1 : kH2;
+        const int j = pass < 3 ? pass * 128 + u : u;
+        float v;
+        if (kind == 0) v = __fadd_rn(bi[j], bh[j]);
+        else if (kind == 1) v = __fadd_rn(bi[H + j], bh[H + j]);
+        else if (kind == 2) v = bi[2 * H + j];
+        else v = bh[2 * H + j];
+        tail[t] = v;
+        return;
+    }
+    t -= kBiasFloats;
+    if (t < kFcFloats) { tail[kBiasFloats + t] = w.w_fc[t]; return; }
+    t -= kFcFloats;
+    if (t < kFc) tail[kBiasFloats + kFcFloats + t] = w.b_fc[t];
+}
+
+int pack_weights_bf16(const fpc_weights *w, void *d_packed, cudaStream_t st)
+{
+    const int n = kBStreamElems + kBiasFloats + kFcFloats + kFc;
+    pack_weights_bf16_kernel<<<(n + 255) / 256, 256, 0, st>>>(*w, (unsigned char *)d_packed);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+// ------------------------------------------------------------------------------------------
+template <int NU> struct SmemB {
+    static constexpr int kX1Bytes = NU * kXK * 2;
+    static constexpr int kH2Bytes = NU * kH2 * 2;
+    static constexpr int offRing = 0;
+    static constexpr int offX1a = offRing + kBStages * kBStageBytes;
+    static constexpr int offX1b = offX1a + kX1Bytes;
+    static constexpr int offH2 = offX1b + kX1Bytes;
+    static constexpr int offBias = offH2 + kH2Bytes;
+    static constexpr int offFc = offBias + kBiasFloats * 4;
+    static constexpr int offRs = offFc + ((kFc * kLdFcB + kFc + 3) / 4) * 16;
+    static constexpr int offRq = offRs + NU * kLdR * 4;
+    static constexpr int offMisc = offRq + NU * 20 * 4;
+    // misc: m1[NU] m2[NU] (float), idx0/idx1/idx2[NU], listA[NU], listB[NU] (int), counts[4], tmem base, pad
+    static constexpr int offBars = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;
+    static constexpr int kNumBars = 2 * kBStages + 3;
+    static constexpr int total = ((offBars + kNumBars * 8 + 127) / 128) * 128;
+    static constexpr int kScratchBytes = kX1Bytes;   // the dead [x | h1] tile doubles as VQ scratch
+};
+
+__device__ __forceinline__ float tanh_fast(float x)
+{
+    float y;
+    asm("tanh.approx.f32 %0, %1;" : "=f"(y) : "f"(x));
+    return y;
+}
+__device__ __forceinline__ float sigmoid_fast(float x)
+{
+    return __fmaf_rn(0.5f, tanh_fast(__fmul_rn(0.5f, x)), 0.5f);
+}
+__device__ __forceinline__ void reg_fence16(uint32_t (&r)[16])
+{
+    asm volatile(""
+                 : "+r"(r[0]), "+r"(r[1]), "+r"(r[2]), "+r"(r[3]), "+r"(r[4]), "+r"(r[5]), "+r"(r[6]), "+r"(r[7]),
+                   "+r"(r[8]), "+r"(r[9]), "+r"(r[10]), "+r"(r[11]), "+r"(r[12]), "+r"(r[13]), "+r"(r[14]), "+r"(r[15]));
+}
+__device__ __forceinline__ float bf16_bits_to_float(unsigned short b) { return __uint_as_float((uint32_t)b << 16); }
+__device__ __forceinline__ unsigned short float_to_bf16_bits(float f) { return __bfloat16_as_ushort(__float2bfloat16_rn(f)); }
+
+// gate epilogue of one 128-unit pass: TMEM (lane = unit, column = utterance) -> new bf16 state
+template <int NU>
+__device__ __forceinline__ void gate_epilogue(uint32_t tb, int q, int hsel, int lane, const float *__restrict__ bias,
+                                              const unsigned char *__restrict__ hold_base,
+                                              unsigned char *__restrict__ hnew_base, int k0)
+{
+    const int jl = 32 * q + lane;
+    const float br = bias[jl], bz = bias[128 + jl], bi = bias[256 + jl], bh = bias[384 + jl];
+    const uint32_t koff = (uint32_t)((k0 + jl) >> 3) * (NU * 16) + (uint32_t)(jl & 7) * 2;
+    constexpr int HALF = NU / 2;
+#pragma unroll 1
+    for (int c = 0; c < HALF / 16; ++c) {
+        const int col0 = hsel * HALF + 16 * c;
+        const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)col0;
+        uint32_t R[16], Z[16], NI[16], NH[16];
+        umma::tmem_ld16(ta, R);
+        umma::tmem_ld16(ta + NU, Z);
+        umma::tmem_ld16(ta + 2 * NU, NI);
+        umma::tmem_ld16(ta + 3 * NU, NH);
+        umma::tmem_ld16_wait(R);
+        reg_fence16(Z); reg_fence16(NI); reg_fence16(NH);
+#pragma unroll
+        for (int t = 0; t < 16; ++t) {
+            const uint32_t off = koff + (uint32_t)(col0 + t) * 16;
+            const float hold = bf16_bits_to_float(*reinterpret_cast<const unsigned short *>(hold_base + off));
+            const float r = sigmoid_fast(__fadd_rn(__uint_as_float(R[t]), br));
+            const float z = sigmoid_fast(__fadd_rn(__uint_as_float(Z[t]), bz));
+            const float n = tanh_fast(__fmaf_rn(r, __fadd_rn(__uint_as_float(NH[t]), bh), __fadd_rn(__uint_as_float(NI[t]), bi)));
+            const float hn = __fmaf_rn(z, __fsub_rn(hold, n), n);
+            *reinterpret_cast<unsigned short *>(hnew_base + off) = float_to_bf16_bits(hn);
+        }
+    }
+}
+
+template <typename T>
+__device__ __forceinline__ void vq_batches(const PackedVq &bk, const char *cbbase, const int *list, int n, const float *rs,
+                                           float *rq, int *idx1, int *idx2, char *scratch, int scratch_bytes, int tid)
+{
+    int sb = 32;
+    while (sb > 8 && (int)vq_fixed_bytes<T>(sb) + 1024 * (int)sizeof(T) > scratch_bytes) sb >>= 1;
+    int vb = (scratch_bytes - (int)vq_fixed_bytes<T>(sb)) / (1024 * (int)sizeof(T));
+    vb = vb > 8 ? 8 : vb;
+    for (int off = 0; off < n; off += sb)
+        vq_search_rows<T>(bk, cbbase, list + off, min(sb, n - off), sb, rs, rq, idx1, idx2, scratch, vb, tid);
+}
+
+template <int NU>
+__global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams P)
+{
+    using S = SmemB<NU>;
+    constexpr int NE = (NU * 20 + kComputeThreads - 1) / kComputeThreads;
+    extern __shared__ __align__(1024) unsigned char smem[];
+    unsigned char *x1[2] = {smem + S::offX1a, smem + S::offX1b};
+    unsigned char *h2t = smem + S::offH2;
+    float *bias = reinterpret_cast<float *>(smem + S::offBias);
+    float *wfc = reinterpret_cast<float *>(smem + S::offFc);
+    float *bfc = wfc + kFc * kLdFcB;
+    float *rs = reinterpret_cast<float *>(smem + S::offRs);
+    float *rq = reinterpret_cast<float *>(smem + S::offRq);
+    float *m1s = reinterpret_cast<float *>(smem + S::offMisc);
+    float *m2s = m1s + NU;
+    int *idx0s = reinterpret_cast<int *>(m2s + NU);
+    int *idx1s = idx0s + NU;
+    int *idx2s = idx1s + NU;
+    int *listA = idx2s + NU;
+    int *listB = listA + NU;
+    int *counts = listB + NU;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(counts + 4);
+    uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::offBars);
+    uint64_t *empty = full + kBStages;
+    uint64_t *acc_full = empty + kBStages;
+    uint64_t *acc_empty = acc_full + 1;
+    uint64_t *act_ready = acc_empty + 1;
+
+    const int tid = threadIdx.x;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
+
+    if (tid == 0) {
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
+        mbar_init(acc_full, 1);
+        mbar_init(acc_empty, kComputeThreads / 32);
+        mbar_init(act_ready, kComputeThreads / 32);
+        mbar_fence_init();
+    }
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 4 * NU);
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = *tmem_slot;
+
+    // ---------------- dedicated warpgroup: TMA producer and MMA issuer ----------------
+    if (warp >= kComputeThreads / 32) {
+        // 256 x 216 + 128 x 64 = 63 488 <= 384 x 168 (the launch allocation): the increase can always be granted
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        if (warp == kComputeThreads / 32 && lane == 0) {
+            const long long total = (long long)my_tiles * P.L * kBStepsPerFrame;
+            const char *src = reinterpret_cast<const char *>(P.wstream);
+            int s = 0, gf = 0;
+            uint32_t wraps = 0;
+            for (long long g = 0; g < total; ++g) {
+                if (wraps > 0) mbar_wait(&empty[s], (wraps - 1) & 1u);
+                mbar_arrive_expect_tx(&full[s], kBStageBytes);
+                bulk_g2s(smem + S::offRing + s * kBStageBytes, src + (size_t)gf * kBStageBytes, kBStageBytes, &full[s]);
+                if (++gf == kBStepsPerFrame) gf = 0;
+                if (++s == kBStages) { s = 0; ++wraps; }
+            }
+        } else if (warp == kComputeThreads / 32 + 1 && lane == 0) {
+            const uint32_t idesc = umma::instr_desc_bf16(128, NU);
+            const uint32_t ring_a = smem_u32(smem + S::offRing);
+            const uint32_t x1a[2] = {smem_u32(x1[0]), smem_u32(x1[1])};
+            const uint32_t h2a = smem_u32(h2t);
+            int s = 0;
+            uint32_t ph = 0, n_act = 0, n_acc = 0;
+            for (int tile = 0; tile < my_tiles; ++tile) {
+                int cur = 0;
+                for (int fr = 0; fr < P.L; ++fr) {
+                    // ---- GRU 1: three passes of 128 hidden units ----
+                    mbar_wait(act_ready, n_act & 1u); ++n_act;
+                    for (int pass = 0; pass < 3; ++pass) {
+                        mbar_wait(acc_empty, (n_acc & 1u) ^ 1u); ++n_acc;
+                        umma::fence_after_sync();
+                        for (int i = 0; i < kBG1Steps; ++i) {
+                            mbar_wait(&full[s], ph);
+                            umma::fence_after_sync();
+                            const uint32_t a0 = ring_a + s * kBStageBytes;
+                            const uint64_t bd = umma::smem_desc(x1a[cur] + (uint32_t)(2 * i) * (NU * 16), NU);
+                            umma::mma_bf16(tb + 0 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                            umma::mma_bf16(tb + 1 * NU, umma::smem_desc(a0 + kBTileBytes, 128), bd, idesc, i > 0);
+                            if (i < 2) umma::mma_bf16(tb + 2 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 0);
+                            else umma::mma_bf16(tb + 3 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 2);
+                            umma::commit(&empty[s]);
+                            if (++s == kBStages) { s = 0; ph ^= 1u; }
+                        }
+                        umma::commit(acc_full);
+                    }
+                    // ---- GRU 2: input h1' (the other [x | h1] tile), hidden h2 ----
+                    mbar_wait(act_ready, n_act & 1u); ++n_act;
+                    mbar_wait(acc_empty, (n_acc & 1u) ^ 1u); ++n_acc;
+                    umma::fence_after_sync();
+                    for (int i = 0; i < kBG2Steps; ++i) {
+                        mbar_wait(&full[s], ph);
+                        umma::fence_after_sync();
+                        const uint32_t a0 = ring_a + s * kBStageBytes;
+                        const bool xp = i < kH1 / 16;
+                        const uint32_t baddr = xp ? x1a[cur ^ 1] + (uint32_t)(4 + 2 * i) * (NU * 16)
+                                                  : h2a + (uint32_t)(2 * (i - kH1 / 16)) * (NU * 16);
+                        const uint64_t bd = umma::smem_desc(baddr, NU);
+                        umma::mma_bf16(tb + 0 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                        umma::mma_bf16(tb + 1 * NU, umma::smem_desc(a0 + kBTileBytes, 128), bd, idesc, i > 0);
+                        if (xp) umma::mma_bf16(tb + 2 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 0);
+                        else umma::mma_bf16(tb + 3 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > kH1 / 16);
+                        umma::commit(&empty[s]);
+                        if (++s == kBStages) { s = 0; ph ^= 1u; }
+                    }
+                    umma::commit(acc_full);
+                    cur ^= 1;
+                }
+            }
+        }
+        return;
+    }
+
+    // ---------------- compute warps ----------------
+    asm volatile("setmaxnreg.inc.sync.aligned.u32 216;");
+    const int q = warp & 3, hsel = warp >> 2;
+    const PackedCodebooks *cbh = reinterpret_cast<const PackedCodebooks *>(P.cb);
+    {
+        const float *tail = reinterpret_cast<const float *>(reinterpret_cast<const char *>(P.wstream) + kBStreamBytes);
+        for (int i = tid; i < kBiasFloats; i += kComputeThreads) bias[i] = tail[i];
+        for (int i = tid; i < kFcFloats; i += kComputeThreads) wfc[(i >> 7) * kLdFcB + (i & 127)] = tail[kBiasFloats + i];
+        if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
+    }
+    uint32_t n_full = 0;
+
+    for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
+        const int b0 = tile * NU;
+        int cur = 0;
+        // h1 = h2 = None -> zeros, frame 0 input all zero (wavernn.py:177-178,189)
+        for (int i = tid; i < S::kX1Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(x1[0])[i] = make_int4(0, 0, 0, 0);
+        for (int i = tid; i < S::kH2Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(h2t)[i] = make_int4(0, 0, 0, 0);
+        for (int i = tid; i < NU * kLdR; i += kComputeThreads) rs[i] = 0.0f;
+        umma::fence_async_smem();
+        named_bar_sync(1, kComputeThreads);
+        if (lane == 0) mbar_arrive(act_ready);
+
+        for (int fr = 0; fr < P.L; ++fr) {
+            float featv[NE], fov[NE], rsv[NE];
+#pragma unroll
+            for (int e2 = 0; e2 < NE; ++e2) {
+                const int e = tid + kComputeThreads * e2;
+                const int u = e / 20, j = e - u * 20;
+                featv[e2] = 0.0f; fov[e2] = 0.0f; rsv[e2] = 0.0f;
+                if (e < NU * 20 && b0 + u < P.B) {
+                    const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                    if (P.mode != kModeDecode) featv[e2] = __ldg(P.feat + fo * 20 + j);
+                    else featv[e2] = j < kFc ? __ldg(P.rq_in + fo * kFc + j) : __ldg(P.pitch_in + fo * 2 + (j - kFc));
+                }
+            }
+            // ---- GRU 1 (wavernn.py:71): gate epilogues of the three passes ----
+#pragma unroll 1
+            for (int pass = 0; pass < 3; ++pass) {
+                mbar_wait(acc_full, n_full & 1u); ++n_full;
+                umma::fence_after_sync();
+                gate_epilogue<NU>(tb, q, hsel, lane, bias + pass * 512, x1[cur], x1[cur ^ 1], 32 + pass * 128);
+                umma::fence_before_sync();
+                if (pass == 2) umma::fence_async_smem();     // h1' is the B operand of GRU 2
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(acc_empty);
+                    if (pass == 2) mbar_arrive(act_ready);
+                }
+            }
+            // ---- GRU 2 (wavernn.py:76), state updated in place ----
+            mbar_wait(acc_full, n_full & 1u); ++n_full;
+            umma::fence_after_sync();
+            gate_epilogue<NU>(tb, q, hsel, lane, bias + 3 * 512, h2t, h2t, 0);
+            umma::fence_before_sync();
+            __syncwarp();
+            if (lane == 0) mbar_arrive(acc_empty);
+            named_bar_sync(1, kComputeThreads);
+
+            // ---- relu, dual_fc, 2*tanh (wavernn.py:87-92); residual (:196) ----
+#pragma unroll
+            for (int e2 = 0; e2 < NE; ++e2) {
+                const int e = tid + kComputeThreads * e2;
+                const int u = e / 20, j = e - u * 20;
+                if (e < NU * 20 && j < kFc) {
+                    float a = bfc[j];
+                    const float *wr = wfc + j * kLdFcB;
+#pragma unroll 4
+                    for (int kc = 0; kc < kH2 / 8; ++kc) {
+                        const int4 pk = *reinterpret_cast<const int4 *>(h2t + (size_t)kc * (NU * 16) + u * 16);
+                        const uint32_t wds[4] = {(uint32_t)pk.x, (uint32_t)pk.y, (uint32_t)pk.z, (uint32_t)pk.w};
+#pragma unroll
+                        for (int h = 0; h < 4; ++h) {
+                            const float lo = __uint_as_float(wds[h] << 16), hi = __uint_as_float(wds[h] & 0xffff0000u);
+                            a = __fmaf_rn(wr[kc * 8 + 2 * h], fmaxf(lo, 0.0f), a);
+                            a = __fmaf_rn(wr[kc * 8 + 2 * h + 1], fmaxf(hi, 0.0f), a);
+                        }
+                    }
+                    const float f = __fmul_rn(2.0f, tanh_c(a));
+                    fov[e2] = f;
+                    if (P.mode != kModeDecode) {
+                        rsv[e2] = __fsub_rn(featv[e2], f);
+                        rs[u * kLdR + 3 + j] = rsv[e2];
+                    }
+                }
+            }
+            if (P.mode != kModeDecode) {
+                for (int i = tid; i < NU * 20; i += kComputeThreads) rq[i] = 0.0f;
+                named_bar_sync(1, kComputeThreads);
+
+                // ---- indicators (:201-212) and the scalar quantiser for c0 (:217-225) ----
+                for (int u = warp; u < NU; u += 8) {
+                    const bool valid = b0 + u < P.B;
+                    float m1 = 0.0f, m2 = 0.0f;
+                    if (lane == 0 && valid) {
+                        if (P.mask == nullptr) {
+                            float sacc = 0.0f;
+#pragma unroll
+                            for (int j = 1; j < kFc; ++j) sacc = __fadd_rn(sacc, fabsf(rs[u * kLdR + 3 + j]));
+                            m1 = fabsf(rs[u * kLdR + 3]) > P.l1 ? 1.0f : 0.0f;
+                            m2 = sacc > P.l2 ? 1.0f : 0.0f;
+                        } else {
+                            const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                            m1 = __ldg(P.mask + fo * 2);
+                            m2 = __ldg(P.mask + fo * 2 + 1);
+                        }
+                    }
+                    m1 = __shfl_sync(0xffffffffu, m1, 0);
+                    m2 = __shfl_sync(0xffffffffu, m2, 0);
+                    int i0 = -1;
+                    if (P.mode == kModeQuantize && valid) {
+                        const PackedScl &sb = (m1 != 0.0f) ? cbh->scl : cbh->blscl;
+                        if (sb.n > 0) {
+                            const float x0 = rs[u * kLdR + 3];
+                            float qv;
+                            if (sb.dtype == FPC_F32) {
+                                float qq;
+                                i0 = warp_scl_nearest<float>(reinterpret_cast<const float *>(P.cb + sb.off), sb.n, x0, lane, qq);
+                                qv = qq;
+                            } else {
+                                double qq;
+                                i0 = warp_scl_nearest<double>(reinterpret_cast<const double *>(P.cb + sb.off), sb.n, x0, lane, qq);
+                                qv = (float)qq;
+                            }
+                            if (lane == 0) rq[u * 20] = qv;
+                        }
+                    }
+                    if (lane == 0) { m1s[u] = m1; m2s[u] = m2; idx0s[u] = i0; idx1s[u] = -1; idx2s[u] = -1; }
+                }
+                named_bar_sync(1, kComputeThreads);
+
+                if (P.mode == kModeQuantize) {
+                    // ---- VQ for c1..c17 (:228-240): rows compacted by branch ----
+                    if (warp == 0) {
+                        int na = 0, nb = 0;
+#pragma unroll
+                        for (int base = 0; base < NU; base += 32) {
+                            const int u = base + lane;
+                            const bool valid = b0 + u < P.B;
+                            const bool above = valid && m2s[u] != 0.0f;
+                            const bool below = valid && !above && cbh->bl.stages > 0;
+                            const unsigned ba = __ballot_sync(0xffffffffu, above);
+                            const unsigned bb = __ballot_sync(0xffffffffu, below);
+                            const unsigned lt = (1u << lane) - 1u;
+                            if (above) listA[na + __popc(ba & lt)] = u;
+                            if (below) listB[nb + __popc(bb & lt)] = u;
+                            na += __popc(ba);
+                            nb += __popc(bb);
+                        }
+                        if (lane == 0) { counts[0] = na; counts[1] = nb; }
+                    }
+                    named_bar_sync(1, kComputeThreads);
+                    const int nA = counts[0], nB = counts[1];
+                    char *scratch = reinterpret_cast<char *>(x1[cur]);   // old [x | h1]: dead once GRU 1 has finished
+                    if (nA > 0) {
+                        if (cbh->vq.dtype == FPC_F32) vq_batches<float>(cbh->vq, P.cb, listA, nA, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                        else vq_batches<double>(cbh->vq, P.cb, listA, nA, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                    }
+                    if (nB > 0) {
+                        if (cbh->bl.dtype == FPC_F32) vq_batches<float>(cbh->bl, P.cb, listB, nB, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                        else vq_batches<double>(cbh->bl, P.cb, listB, nB, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                    }
+                }
+            } else {
+                named_bar_sync(1, kComputeThreads);
+            }
+
+            // ---- feedback (:242 / :252), outputs, next input frame (bf16 B-operand tile) ----
+            unsigned char *xn = x1[cur ^ 1];
+#pragma unroll
+            for (int e2 = 0; e2 < NE; ++e2) {
+                const int e = tid + kComputeThreads * e2;
+                const int u = e / 20, j = e - u * 20;
+                if (e < NU * 20) {
+                    const bool valid = b0 + u < P.B;
+                    const size_t fo = (size_t)(b0 + u) * P.L + fr;
+                    float cin;
+                    if (j < kFc) {
+                        float ro, rqo, ruo;
+                        if (P.mode == kModeQuantize) {
+                            rqo = rq[u * 20 + j];
+                            ro = rsv[e2];
+                            ruo = 0.0f;
+                            cin = __fadd_rn(fov[e2], rqo);
+                        } else if (P.mode == kModeResidual) {
+                            const float m = j == 0 ? m1s[u] : m2s[u];
+                            ruo = __fmul_rn(rsv[e2], __fsub_rn(1.0f, m));
+                            ro = __fmul_rn(rsv[e2], m);
+                            rqo = 0.0f;
+                            cin = __fadd_rn(fov[e2], ro);
+                        } else {
+                            ro = rqo = ruo = 0.0f;
+                            cin = __fadd_rn(fov[e2], featv[e2]);
+                        }
+                        if (valid && P.mode != kModeDecode) {
+                            P.r[fo * kFc + j] = ro;
+                            P.r_qtz[fo * kFc + j] = rqo;
+                            if (P.r_under) P.r_under[fo * kFc + j] = ruo;
+                        }
+                    } else {
+                        cin = featv[e2];
+                    }
+                    *reinterpret_cast<unsigned short *>(xn + (size_t)(j >> 3) * (NU * 16) + u * 16 + (j & 7) * 2) = float_to_bf16_bits(cin);
+                    if (valid) P.c_in[fo * 20 + j] = cin;
+                }
+            }
+            // K padding 20..31 of the x part: the tile served as VQ scratch, so rewrite the zeros
+            for (int i = tid; i < NU * 12; i += kComputeThreads) {
+                const int u = i / 12, k = 20 + (i - u * 12);
+                *reinterpret_cast<unsigned short *>(xn + (size_t)(k >> 3) * (NU * 16) + u * 16 + (k & 7) * 2) = 0;
+            }
+            if (P.mode != kModeDecode && tid < NU && b0 + tid < P.B) {
+                const size_t fo = (size_t)(b0 + tid) * P.L + fr;
+                const float m1 = m1s[tid], m2 = m2s[tid];
+                if (P.ind1) P.ind1[fo] = P.mask ? 0.0f : m1;
+                if (P.ind2) P.ind2[fo] = P.mask ? 0.0f : m2;
+                if (P.idx) {
+                    int4 v;
+                    v.x = idx0s[tid]; v.y = idx1s[tid]; v.z = idx2s[tid];
+                    v.w = (m1 != 0.0f ? 1 : 0) | (m2 != 0.0f ? 2 : 0);
+                    *reinterpret_cast<int4 *>(P.idx + fo * 4) = v;
+                }
+            }
+            umma::fence_async_smem();
+            named_bar_sync(1, kComputeThreads);
+            if (lane == 0 && fr + 1 < P.L) mbar_arrive(act_ready);
+            cur ^= 1;
+        }
+    }
+    named_bar_sync(1, kComputeThreads);
+    if (warp == 0) umma::tmem_dealloc(tb, 4 * NU);
+}
+
+template <int NU>
+static int launch_encode_bf16(const EncodeParams &P, int grid, cudaStream_t st)
+{
+    using S = SmemB<NU>;
+    static bool configured = false;
+    if (!configured) {
+        FPC_CUDA_TRY(cudaFuncSetAttribute(encode_bf16_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total));
+        configured = true;
+    }
+    encode_bf16_kernel<NU><<<grid, kBThreads, S::total, st>>>(P);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu)
+{
+    const int sms = num_sms();
+    if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
+    int nu = force_nu;
+    if (nu <= 0) {
+        // tile height that minimises waves x per-tile cost (+6: per-frame fixed work of a tile)
+        double best = 1e30;
+        const int cand[2] = {32, 64};
+        for (int c = 0; c < 2; ++c) {
+            const int tiles = (P.B + cand[c] - 1) / cand[c];
+            const int waves = (tiles + sms - 1) / sms;
+            const double cost = (double)waves * (cand[c] + 6.0);
+            if (cost < best - 1e-9) { best = cost; nu = cand[c]; }
+        }
+    }
+    P.ntiles = (P.B + nu - 1) / nu;
+    const int grid = P.ntiles < sms ? P.ntiles : sms;
+    if (nu == 32) return launch_encode_bf16<32>(P, grid, st);
+    if (nu == 64) return launch_encode_bf16<64>(P, grid, st);
+    return FPC_ERR_ARG;
+}
+
+}  // namespace fpc

@@ -3,6 +3,7 @@
 // (/root/reference/src/models/wavernn.py:37-38,48-52) and the .npy files loaded at
 // quantization/vq_func.py:141,171.
 #include "fpc_common.cuh"
+#include "fpc_encode.cuh"
 
 namespace fpc {
 
@@ -205,6 +206,7 @@ int fpc_pack_codebooks(const fpc_codebooks *cb, void *d_packed, size_t packed_by
 size_t fpc_packed_weights_bytes(int precision)
 {
     if (precision == FPC_PREC_FP32) return (size_t)kPackedF32Floats * 4;
+    if (precision == FPC_PREC_BF16) return packed_bf16_bytes();
     return 0;
 }
 
@@ -221,6 +223,10 @@ int fpc_pack_weights(const fpc_weights *w, int precision, void *d_packed, size_t
         pack_weights_f32_kernel<<<(n + 255) / 256, 256, 0, st>>>(*w, (float *)d_packed);
         FPC_LAUNCH_CHECK();
         return FPC_OK;
+    }
+    if (precision == FPC_PREC_BF16) {
+        if (packed_bytes < packed_bf16_bytes()) return FPC_ERR_WORKSPACE;
+        return pack_weights_bf16(w, d_packed, st);
     }
     return FPC_ERR_UNSUPPORTED;
 }

@@ -1,0 +1,123 @@
+"""bf16 mode (GRU gate contractions on tcgen05 tensor cores, bf16 recurrent state).
+
+A bf16 predictor is a different (rounded) predictor, so indices cannot be required to equal the
+fp32 reference's: in a closed loop one flipped index changes every later frame of that utterance.
+What is required and tested:
+  * exact properties -- run-to-run determinism, independence of an utterance from its position in
+    the batch / the tile height, and decode(encode(x)) == c_in bit for bit (the receiver replays the
+    same bf16 recurrence, which is what a codec needs);
+  * the quantiser arithmetic stays exact: every coded residual is the exact codeword the reference's
+    search would pick FOR THE RESIDUAL THE KERNEL SAW (checked by re-quantising r with the oracle);
+  * stated tolerance against the fp32 oracle: predictor output within 3e-2 abs while the inputs are
+    still identical (frame 0 .. first index divergence), teacher-forced residual mode within 3e-2 abs.
+The measured index agreement is printed (and recorded in DESIGN.md), not asserted beyond a floor.
+"""
+import os
+import tempfile
+
+import numpy as np
+import pytest
+
+from helpers import oracle_codebooks
+
+pytestmark = pytest.mark.gpu
+PRED_TOL = 3e-2
+
+
+@pytest.fixture(scope="module")
+def torch_cuda():
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("GPU tests need a CUDA device")
+    return torch
+
+
+@pytest.fixture(scope="module")
+def model16(torch_cuda, state_dict):
+    import fpc_native
+    from models.wavernn import Wavernn
+    m = Wavernn(20, 384, 128, 18).eval()
+    m.load_state_dict(state_dict)
+    m = m.cuda()
+    m.precision = fpc_native.FPC_PREC_BF16
+    return m
+
+
+@pytest.fixture(scope="module")
+def cfgdir(synth):
+    with tempfile.TemporaryDirectory(prefix="fpc_b16_") as d:
+        cbs = synth.make_codebooks(0)
+        yield synth.save_codebooks(cbs, d), cbs
+
+
+def encode(torch, model, cfg, feat, l1, l2, qtz=True):
+    with torch.no_grad():
+        out = model.encoder(cfg, torch.from_numpy(feat).cuda(), None, l1, l2, None, None, qtz)
+    torch.cuda.synchronize()
+    d = {k: v.cpu().numpy() for k, v in zip(("c_in", "r", "r_qtz", "r_under", "ind1", "ind2"), out[:6])}
+    d["idx"] = model.last_result.idx.cpu().numpy()
+    return d
+
+
+@pytest.mark.parametrize("B,L", [(5, 30), (70, 40), (200, 12)])
+def test_bf16_exact_properties(torch_cuda, model16, synth, cfgdir, oracle, B, L):
+    torch = torch_cuda
+    cfg, cbs = cfgdir
+    feat = synth.make_features(B, L, first_utt=8000)
+    a = encode(torch, model16, cfg, feat, 0.25, 2.1)
+    b = encode(torch, model16, cfg, feat, 0.25, 2.1)
+    for k in a:
+        assert np.array_equal(a[k], b[k]), "bf16 mode is not deterministic in %s" % k
+    assert np.isfinite(a["c_in"]).all()
+    # position / tile-height independence: a sub-batch in another order gives the same rows
+    sel = list(range(B - 1, -1, -3))
+    c = encode(torch, model16, cfg, feat[sel], 0.25, 2.1)
+    assert np.array_equal(c["idx"], a["idx"][sel]) and np.array_equal(c["c_in"], a["c_in"][sel])
+    # receiver: replaying the quantised residual reproduces the decoded frames bit for bit
+    fd = torch.from_numpy(feat).cuda()
+    dec = model16.decoder(cfg, fd, torch.from_numpy(a["r_qtz"]).cuda()).cpu().numpy()
+    assert np.array_equal(dec, a["c_in"])
+    # the quantisers are exact on the residual the kernel produced
+    C = oracle_codebooks(oracle, cbs)
+    r = a["r"].reshape(-1, 18)
+    idx = a["idx"].reshape(-1, 4)
+    above = (idx[:, 3] & 2) != 0
+    q_ab, i_ab = oracle.vq_quantize(cbs["cb_path"], r[above, 1:])
+    assert np.array_equal(i_ab, idx[above, 1:3])
+    assert np.array_equal(q_ab.astype(np.float32), a["r_qtz"].reshape(-1, 18)[above, 1:])
+    q_bl, i_bl = oracle.vq_quantize(cbs["bl_cb_path"], r[~above, 1:])
+    assert np.array_equal(i_bl[:, 0], idx[~above, 1])
+    sa = (idx[:, 3] & 1) != 0
+    qs, si = oracle.scl_quantize(cbs["scl_cb_path"], r[sa, 0])
+    assert np.array_equal(si, idx[sa, 0])
+    # thresholds are applied exactly to that residual (fp32, strict >)
+    assert np.array_equal(np.abs(r[:, 0]) > np.float32(0.25), sa)
+
+
+def test_bf16_vs_fp32_oracle_tolerance(torch_cuda, model16, synth, cfgdir, oracle, oracle_weights):
+    torch = torch_cuda
+    cfg, cbs = cfgdir
+    B, L = 64, 200
+    feat = synth.make_features(B, L, first_utt=8100)
+    C = oracle_codebooks(oracle, cbs)
+    for l1, l2, name in ((0.25, 2.1, "calibrated"), (0.09, 0.28, "README")):
+        g = encode(torch, model16, cfg, feat, l1, l2)
+        o = oracle.encode(oracle_weights, C, feat, l1, l2)
+        same = np.all(g["idx"] == o["idx"], axis=-1)                    # (B, L)
+        first_div = np.where(same.all(1), L, np.argmin(same, axis=1))    # frames until first divergence
+        fo_g = g["c_in"][:, :, :18] - g["r_qtz"]
+        fo_o = o["c_in"][:, :, :18] - o["r_qtz"]
+        # while every earlier index agreed the two predictors saw identical inputs
+        ok = np.arange(L)[None, :] <= first_div[:, None]
+        err = np.abs(fo_g - fo_o).max(-1)
+        print("\nbf16 vs fp32 oracle (%s thresholds): index agreement %.4f of frames, median frames to first divergence %d, "
+              "predictor max abs err before divergence %.3g, decoded-feature rms diff %.3g"
+              % (name, same.mean(), int(np.median(first_div)), err[ok].max(), np.sqrt(np.mean((g["c_in"] - o["c_in"]) ** 2))))
+        assert err[ok].max() <= PRED_TOL
+        assert same[:, 0].mean() >= 0.8       # frame 0: identical (zero) state, only bf16 weight rounding
+    # teacher-forced flavour: residual generation mode feeds back feat itself whenever above threshold
+    g = encode(torch, model16, {}, feat, 0.0, 0.0, qtz=False)
+    o = oracle.encode(oracle_weights, None, feat, 0.0, 0.0, qtz=False)
+    err = np.abs(g["r"] - o["r"]).max()
+    print("bf16 residual mode (all frames above threshold => teacher forced): max abs residual diff %.3g" % err)
+    assert err <= PRED_TOL

@@ -2,6 +2,7 @@
 #include "fpc_common.cuh"
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
+#include "fpc_vq_screen.cuh"
 #include "fpc_encode.cuh"
 
 namespace fpc {
@@ -14,7 +15,7 @@ constexpr int kQTile = 32;
 template <typename T>
 __global__ void __launch_bounds__(kComputeThreads, 1)
 vq_quantize_kernel(const float *__restrict__ x, long n, const char *__restrict__ cb, int which, T *__restrict__ q,
-                   int32_t *__restrict__ idx)
+                   int32_t *__restrict__ idx, int scratch_bytes)
 {
     extern __shared__ __align__(128) unsigned char smem[];
     float *rs = reinterpret_cast<float *>(smem);                 // [32][24]
@@ -36,7 +37,7 @@ vq_quantize_kernel(const float *__restrict__ x, long n, const char *__restrict__
         }
         if (tid < kQTile) list[tid] = tid;
         __syncthreads();
-        vq_search_rows<T>(bk, cb, list, nb, kQTile, rs, rq, idx1, idx2, scratch, 8, tid, q + base * kDim);
+        vq_search_rows_screened<T>(bk, cb, list, nb, kQTile, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, q + base * kDim);
         if (tid < nb) {
             idx[(base + tid) * bk.stages] = idx1[tid];
             if (bk.stages > 1) idx[(base + tid) * bk.stages + 1] = idx2[tid];
@@ -177,7 +178,7 @@ int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebo
             cfg = true;
         }
         vq_quantize_kernel<float><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
-                                                                          (float *)d_q, d_idx);
+                                                                          (float *)d_q, d_idx, (int)(smem - fixed));
     } else if (dtype == FPC_F64) {
         const size_t smem = fixed + vq_fixed_bytes<double>(kQTile) + 8 * 1024 * sizeof(double);
         static bool cfg = false;
@@ -186,7 +187,7 @@ int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebo
             cfg = true;
         }
         vq_quantize_kernel<double><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
-                                                                           (double *)d_q, d_idx);
+                                                                           (double *)d_q, d_idx, (int)(smem - fixed));
     } else {
         return FPC_ERR_CODEBOOK;
     }

@@ -57,9 +57,14 @@ constexpr int kFcFloats = kFc * kH2;                     // 2304
 constexpr int kPackedF32Floats = ((kStreamFloats + kBiasFloats + kFcFloats + kFc + 3) / 4) * 4;
 
 struct PackedVq {        // one VQ codebook file
-    int dtype, stages, K, pad;
-    long long off_t[2];   // byte offset of stage s transposed [17][K]
-    long long off_r[2];   // byte offset of stage s row-major  [K][17]
+    int dtype, stages, K, Kp;   // Kp = K rounded up to a multiple of 4
+    long long off_t[2];   // byte offset of stage s transposed [17][K]   (file dtype)
+    long long off_r[2];   // byte offset of stage s row-major  [K][17]   (file dtype)
+    // screening data (fpc_vq_screen.cuh), always fp32:
+    long long off_f[2];   // stage s transposed shadow [17][Kp], (float)c, zero padded
+    long long off_n[2];   // stage s squared norms [Kp], padded with 3e38
+    long long off_g;      // Gram table [K][Kp] = 2 * <c0_k0, c1_k1>   (2-stage books)
+    long long off_cmax;   // float[2]: upper bounds of max_k ||c_k|| per stage
 };
 struct PackedScl {
     int dtype, n;
@@ -69,8 +74,10 @@ struct PackedCodebooks {  // header at offset 0 of the packed codebook image
     PackedVq vq, bl;
     PackedScl scl, blscl;
 };
-constexpr size_t kCbHeaderBytes = 256;
-constexpr size_t kCbVqMaxBytes = (size_t)2 * FPC_MAX_VQ_ENTRIES * kDim * 8 * 2;   // both layouts, f64
+constexpr size_t kCbHeaderBytes = 512;
+constexpr size_t kCbVqMaxBytes = (size_t)2 * FPC_MAX_VQ_ENTRIES * kDim * 8 * 2    // both layouts, f64
+                                 + (size_t)2 * (kDim + 1) * FPC_MAX_VQ_ENTRIES * 4   // fp32 shadows + norms
+                                 + (size_t)FPC_MAX_VQ_ENTRIES * FPC_MAX_VQ_ENTRIES * 4 + 8192;   // Gram table, cmax, alignment slack
 constexpr size_t kCbSclMaxBytes = (size_t)FPC_MAX_SCL_ENTRIES * 8;
 constexpr size_t kPackedCbBytes = kCbHeaderBytes + 2 * kCbVqMaxBytes + 2 * kCbSclMaxBytes;
 

@@ -23,6 +23,7 @@
 #include "fpc_math.cuh"
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
+#include "fpc_vq_screen.cuh"
 #include "fpc_encode.cuh"
 #include "fpc_umma.cuh"
 
@@ -175,18 +176,6 @@ __device__ __forceinline__ void gate_epilogue(uint32_t tb, int q, int hsel, int 
             *reinterpret_cast<unsigned short *>(hnew_base + off) = float_to_bf16_bits(hn);
         }
     }
-}
-
-template <typename T>
-__device__ __forceinline__ void vq_batches(const PackedVq &bk, const char *cbbase, const int *list, int n, const float *rs,
-                                           float *rq, int *idx1, int *idx2, char *scratch, int scratch_bytes, int tid)
-{
-    int sb = 32;
-    while (sb > 8 && (int)vq_fixed_bytes<T>(sb) + 1024 * (int)sizeof(T) > scratch_bytes) sb >>= 1;
-    int vb = (scratch_bytes - (int)vq_fixed_bytes<T>(sb)) / (1024 * (int)sizeof(T));
-    vb = vb > 8 ? 8 : vb;
-    for (int off = 0; off < n; off += sb)
-        vq_search_rows<T>(bk, cbbase, list + off, min(sb, n - off), sb, rs, rq, idx1, idx2, scratch, vb, tid);
 }
 
 template <int NU>
@@ -460,13 +449,13 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     named_bar_sync(1, kComputeThreads);
                     const int nA = counts[0], nB = counts[1];
                     char *scratch = reinterpret_cast<char *>(x1[cur]);   // old [x | h1]: dead once GRU 1 has finished
-                    if (nA > 0) {
-                        if (cbh->vq.dtype == FPC_F32) vq_batches<float>(cbh->vq, P.cb, listA, nA, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
-                        else vq_batches<double>(cbh->vq, P.cb, listA, nA, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
-                    }
-                    if (nB > 0) {
-                        if (cbh->bl.dtype == FPC_F32) vq_batches<float>(cbh->bl, P.cb, listB, nB, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
-                        else vq_batches<double>(cbh->bl, P.cb, listB, nB, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                    // one call site for both books (above / below threshold): a single inlined copy of the search
+#pragma unroll 1
+                    for (int book = 0; book < 2; ++book) {
+                        const int nrows = book ? nB : nA;
+                        if (nrows > 0)
+                            vq_dispatch_screened(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, NU, rs, rq, idx1s, idx2s,
+                                                 scratch, S::kScratchBytes, tid);
                     }
                 }
             } else {

@@ -24,6 +24,7 @@
 #include "fpc_math.cuh"
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
+#include "fpc_vq_screen.cuh"
 #include "fpc_encode.cuh"
 
 namespace fpc {
@@ -324,8 +325,14 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                     named_bar_sync(1, kComputeThreads);
                     const int nA = counts[0], nB = counts[1];
                     char *scratch = reinterpret_cast<char *>(cur);   // dead state set (see Smem)
-                    if (nA > 0) vq_dispatch(cbh->vq, P.cb, listA, nA, MT, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
-                    if (nB > 0) vq_dispatch(cbh->bl, P.cb, listB, nB, MT, rs, rq, idx1s, idx2s, scratch, S::kScratchBytes, tid);
+                    // one call site for both books (above / below threshold): a single inlined copy of the search
+#pragma unroll 1
+                    for (int book = 0; book < 2; ++book) {
+                        const int nrows = book ? nB : nA;
+                        if (nrows > 0)
+                            vq_dispatch_screened(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, MT, rs, rq, idx1s, idx2s,
+                                                 scratch, S::kScratchBytes, tid);
+                    }
                 }
             } else {
                 named_bar_sync(1, kComputeThreads);

@@ -85,6 +85,43 @@ __global__ void pack_vq_kernel(const T *__restrict__ src, int stages, int K, T *
     dr[r] = v;
 }
 
+// screening data of one stage: fp32 shadow [17][Kp], squared norms [Kp] (float64 sum, rounded),
+// and an upper bound of max ||c|| (atomicMax on the bit pattern of a non-negative float)
+template <typename T>
+__global__ void pack_screen_kernel(const T *__restrict__ src /* [K][17] of this stage */, int K, int Kp,
+                                   float *__restrict__ shadow, float *__restrict__ norms, float *__restrict__ cmax)
+{
+    const int k = blockIdx.x * blockDim.x + threadIdx.x;
+    if (k >= Kp) return;
+    if (k >= K) {
+        for (int d = 0; d < kDim; ++d) shadow[(size_t)d * Kp + k] = 0.0f;
+        norms[k] = 3.0e38f;
+        return;
+    }
+    double n2 = 0.0;
+    for (int d = 0; d < kDim; ++d) {
+        const double c = (double)src[(size_t)k * kDim + d];
+        shadow[(size_t)d * Kp + k] = (float)c;
+        n2 += c * c;
+    }
+    norms[k] = (float)n2;
+    const float nb = __fmul_ru(__fsqrt_ru(__double2float_ru(n2)), 1.0000001f);
+    atomicMax(reinterpret_cast<unsigned int *>(cmax), __float_as_uint(nb));
+}
+
+// Gram table of a two-stage book: G[k0][k1] = 2 <c0_k0, c1_k1>, float64 dot rounded to fp32
+template <typename T>
+__global__ void pack_gram_kernel(const T *__restrict__ c0, const T *__restrict__ c1, int K, int Kp, float *__restrict__ G)
+{
+    const long long t = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    if (t >= (long long)K * Kp) return;
+    const int k0 = (int)(t / Kp), k1 = (int)(t - (long long)k0 * Kp);
+    double acc = 0.0;
+    if (k1 < K)
+        for (int d = 0; d < kDim; ++d) acc += (double)c0[(size_t)k0 * kDim + d] * (double)c1[(size_t)k1 * kDim + d];
+    G[t] = (float)(2.0 * acc);
+}
+
 template <typename T>
 __global__ void copy_kernel(const T *__restrict__ src, int n, T *__restrict__ dst)
 {
@@ -114,8 +151,9 @@ static int check_scl(const void *p, int dtype, int n, bool required)
 static int pack_one_vq(const void *src, int dtype, int stages, int K, char *base, size_t &cursor, PackedVq &h,
                        cudaStream_t st)
 {
-    h.dtype = dtype; h.stages = stages; h.K = K; h.pad = 0;
+    h.dtype = dtype; h.stages = stages; h.K = K; h.Kp = (K + 3) & ~3;
     h.off_t[0] = h.off_t[1] = h.off_r[0] = h.off_r[1] = 0;
+    h.off_f[0] = h.off_f[1] = h.off_n[0] = h.off_n[1] = h.off_g = h.off_cmax = 0;
     if (stages == 0) return FPC_OK;
     size_t es = dtype == FPC_F32 ? 4 : 8;
     size_t one = (((size_t)K * kDim * es) + 255) / 256 * 256;
@@ -134,6 +172,34 @@ static int pack_one_vq(const void *src, int dtype, int stages, int K, char *base
                                                        (double *)(base + h.off_r[0]), (double *)(base + h.off_t[1]),
                                                        (double *)(base + h.off_r[1]));
     FPC_LAUNCH_CHECK();
+    // ---- screening data ----
+    const int Kp = h.Kp;
+    h.off_cmax = (long long)cursor; cursor += 256;
+    FPC_CUDA_TRY(cudaMemsetAsync(base + h.off_cmax, 0, 256, st));
+    for (int s = 0; s < stages; ++s) {
+        h.off_f[s] = (long long)cursor; cursor += (((size_t)kDim * Kp * 4) + 255) / 256 * 256;
+        h.off_n[s] = (long long)cursor; cursor += (((size_t)Kp * 4) + 255) / 256 * 256;
+        float *cm = (float *)(base + h.off_cmax) + s;
+        if (dtype == FPC_F32)
+            pack_screen_kernel<float><<<(Kp + 127) / 128, 128, 0, st>>>((const float *)src + (size_t)s * K * kDim, K, Kp,
+                                                                         (float *)(base + h.off_f[s]), (float *)(base + h.off_n[s]), cm);
+        else
+            pack_screen_kernel<double><<<(Kp + 127) / 128, 128, 0, st>>>((const double *)src + (size_t)s * K * kDim, K, Kp,
+                                                                          (float *)(base + h.off_f[s]), (float *)(base + h.off_n[s]), cm);
+        FPC_LAUNCH_CHECK();
+    }
+    if (stages == 2) {
+        h.off_g = (long long)cursor; cursor += (((size_t)K * Kp * 4) + 255) / 256 * 256;
+        const long long n2 = (long long)K * Kp;
+        const int gb = (int)((n2 + 255) / 256);
+        if (dtype == FPC_F32)
+            pack_gram_kernel<float><<<gb, 256, 0, st>>>((const float *)src, (const float *)src + (size_t)K * kDim, K, Kp,
+                                                         (float *)(base + h.off_g));
+        else
+            pack_gram_kernel<double><<<gb, 256, 0, st>>>((const double *)src, (const double *)src + (size_t)K * kDim, K, Kp,
+                                                          (float *)(base + h.off_g));
+        FPC_LAUNCH_CHECK();
+    }
     return FPC_OK;
 }
 

@@ -84,7 +84,7 @@ __device__ __forceinline__ void merge_parts(const VqPart<T> *__restrict__ p, int
 // Every thread of the 256 must call this with identical arguments (barrier id 1 is used).
 // ------------------------------------------------------------------------------------------
 template <typename T>
-__device__ void vq_search_rows(const PackedVq &bk, const char *__restrict__ cbbase, const int *__restrict__ list, int n,
+__device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__restrict__ cbbase, const int *__restrict__ list, int n,
                                int maxn, const float *__restrict__ rs, float *__restrict__ rq, int *__restrict__ idx1,
                                int *__restrict__ idx2, char *__restrict__ scratch, int vb, int tid,
                                T *__restrict__ qglobal = nullptr)

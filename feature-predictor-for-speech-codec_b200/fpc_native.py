@@ -9,7 +9,7 @@ import ctypes
 import os
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-_LIB_PATH = os.path.join(_HERE, "csrc", "libfpc_b200.so")
+_LIB_PATH = os.environ.get("FPC_B200_LIB") or os.path.join(_HERE, "csrc", "libfpc_b200.so")   # override: A/B builds
 _lib = None
 
 FPC_PREC_FP32, FPC_PREC_BF16 = 0, 1

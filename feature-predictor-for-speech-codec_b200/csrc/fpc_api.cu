@@ -82,9 +82,14 @@ __global__ void index_histogram_kernel(const int4 *__restrict__ idx, long n, uns
 
 }  // namespace fpc
 
+namespace fpc { long long *g_phase_buffer = nullptr; }
+
 using namespace fpc;
 
 extern "C" {
+
+/* debug: 8 int64 counters (device memory, zeroed by the caller); CTA 0 adds the cycles it spent per phase */
+int fpc_debug_set_phase_buffer(void *d_buf) { g_phase_buffer = (long long *)d_buf; return FPC_OK; }
 
 size_t fpc_encode_workspace_bytes(int B, int L, int precision)
 {
@@ -115,6 +120,7 @@ int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, con
     P.mode = io->qtz ? kModeQuantize : kModeResidual;
     P.l1 = io->l1; P.l2 = io->l2;
     P.ntiles = 0;
+    P.prof = g_phase_buffer;
     if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }
@@ -134,7 +140,7 @@ int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *
     P.rq_in = d_r_qtz; P.pitch_in = d_pitch;
     P.c_in = d_c_out; P.r = nullptr; P.r_qtz = nullptr; P.r_under = nullptr;
     P.ind1 = nullptr; P.ind2 = nullptr; P.idx = nullptr;
-    P.B = B; P.L = L; P.mode = kModeDecode; P.l1 = 0.0f; P.l2 = 0.0f; P.ntiles = 0;
+    P.B = B; P.L = L; P.mode = kModeDecode; P.l1 = 0.0f; P.l2 = 0.0f; P.ntiles = 0; P.prof = nullptr;
     if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }

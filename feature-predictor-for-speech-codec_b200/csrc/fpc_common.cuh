@@ -55,6 +55,11 @@ constexpr int kStreamFloats = kGroupsPerFrame * kGroupFloats;
 constexpr int kBiasFloats = 4 * 4 * 128;                 // [3 GRU1 passes + GRU2][br,bz,bni,bnh][128]
 constexpr int kFcFloats = kFc * kH2;                     // 2304
 constexpr int kPackedF32Floats = ((kStreamFloats + kBiasFloats + kFcFloats + kFc + 3) / 4) * 4;
+// Every CTA re-reads the whole weight image every frame, nearly in lock-step, so each L2 line of a single
+// image takes ~150 back-to-back requests.  The image is therefore stored kWeightReplicas times (still
+// L2-resident) and CTA b streams replica b % kWeightReplicas, spreading the requests over more L2 lines.
+constexpr int kWeightReplicas = 8;
+constexpr size_t kPackedF32ReplicaBytes = (((size_t)kPackedF32Floats * 4 + 255) / 256) * 256;
 
 struct PackedVq {        // one VQ codebook file
     int dtype, stages, K, Kp;   // Kp = K rounded up to a multiple of 4

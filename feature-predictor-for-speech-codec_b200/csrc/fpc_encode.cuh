@@ -18,6 +18,7 @@ struct EncodeParams {
     int B, L, mode;
     float l1, l2;
     int ntiles;
+    long long *prof;        // optional debug buffer: per-phase cycle totals of CTA 0 (fpc_debug_set_phase_buffer)
 };
 
 int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu);
@@ -26,5 +27,7 @@ int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu);
 size_t packed_bf16_bytes();
 int pack_weights_bf16(const fpc_weights *w, void *d_packed, cudaStream_t st);
 int num_sms();
+extern long long *g_phase_buffer;   // device pointer or null
+enum { kPhGru = 0, kPhFc = 1, kPhScalar = 2, kPhVq = 3, kPhOut = 4, kPhFrames = 5, kPhVqDbg = 6 /* 8 counters of the search */, kPhCount = 16 };
 
 }  // namespace fpc

@@ -178,7 +178,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == kComputeThreads / 32 && lane == 0) {
             const long long total = (long long)my_tiles * P.L * kGroupsPerFrame;
-            const char *src = reinterpret_cast<const char *>(P.wstream);
+            const char *src = reinterpret_cast<const char *>(P.wstream) + (size_t)(blockIdx.x % kWeightReplicas) * kPackedF32ReplicaBytes;
             int s = 0, gf = 0;
             uint32_t wraps = 0;
             for (long long g = 0; g < total; ++g) {
@@ -206,6 +206,9 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
         if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
     }
     Pipe pp{0, 0u};
+    const bool prof = P.prof != nullptr && tid == 0;
+    long long pt[kPhCount] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
+#define FPC_PHASE(ph) do { if (prof) { const long long t_ = clock64(); pt[ph] += t_ - pt0; pt0 = t_; } } while (0)
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int b0 = tile * MT;
@@ -232,6 +235,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
             float *h1c = cur, *h2c = cur + MT * kLd1;
             float *h1n = nxt, *h2n = nxt + MT * kLd1;
 
+            if (prof) pt0 = clock64();
             // ---- GRU 1: three passes of 128 hidden units (wavernn.py:71) ----
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
@@ -245,6 +249,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                          h2n + tg * kLd2 + 2 * ug, kLd2, bias + 3 * 512, ring, full, empty, pp, ug, lane);
             named_bar_sync(1, kComputeThreads);
 
+            FPC_PHASE(kPhGru);
             // ---- relu, dual_fc, 2*tanh (wavernn.py:87-92); residual (:196) ----
 #pragma unroll
             for (int q = 0; q < NE; ++q) {
@@ -268,6 +273,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                 for (int i = tid; i < MT * 20; i += kComputeThreads) rq[i] = 0.0f;
                 named_bar_sync(1, kComputeThreads);
 
+                FPC_PHASE(kPhFc);
                 // ---- indicators (:201-212) and the scalar quantiser for c0 (:217-225) ----
                 for (int u = warp; u < MT; u += 8) {
                     const bool valid = b0 + u < P.B;
@@ -309,6 +315,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                 }
                 named_bar_sync(1, kComputeThreads);
 
+                FPC_PHASE(kPhScalar);
                 if (P.mode == kModeQuantize) {
                     // ---- VQ for c1..c17 (:228-240): compact the tile rows by branch ----
                     if (warp == 0) {
@@ -331,13 +338,14 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                         const int nrows = book ? nB : nA;
                         if (nrows > 0)
                             vq_dispatch_screened(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, MT, rs, rq, idx1s, idx2s,
-                                                 scratch, S::kScratchBytes, tid);
+                                                 scratch, S::kScratchBytes, tid, prof ? pt + kPhVqDbg : nullptr);
                     }
                 }
             } else {
                 named_bar_sync(1, kComputeThreads);
             }
 
+            FPC_PHASE(kPhVq);
             // ---- feedback (:242 / :252), outputs, next input frame ----
 #pragma unroll
             for (int q = 0; q < NE; ++q) {
@@ -390,9 +398,14 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                 }
             }
             named_bar_sync(1, kComputeThreads);
+            FPC_PHASE(kPhOut);
+            if (prof) pt[kPhFrames] += 1;
             float *t = cur; cur = nxt; nxt = t;
         }
     }
+    if (prof)
+        for (int i = 0; i < kPhCount; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof) + (size_t)blockIdx.x * kPhCount + i, (unsigned long long)pt[i]);
+#undef FPC_PHASE
 }
 
 template <int TU>

@@ -15,9 +15,10 @@ unsigned long long g_launch_count = 0;
 //   group g of a pass -> [slot c = gate*2 + e][unit pair ug 0..63][kk 0..3]
 //   hidden unit j = pass*128 + 2*ug + e ; k = 4*(group index within part) + kk
 // ------------------------------------------------------------------------------------------
-__global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out)
+__global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out0)
 {
     int t = blockIdx.x * blockDim.x + threadIdx.x;
+    float *__restrict__ out = reinterpret_cast<float *>(reinterpret_cast<char *>(out0) + (size_t)blockIdx.y * kPackedF32ReplicaBytes);
     if (t < kStreamFloats) {
         int g = t / kGroupFloats;
         int r = t - g * kGroupFloats;
@@ -271,7 +272,7 @@ int fpc_pack_codebooks(const fpc_codebooks *cb, void *d_packed, size_t packed_by
 
 size_t fpc_packed_weights_bytes(int precision)
 {
-    if (precision == FPC_PREC_FP32) return (size_t)kPackedF32Floats * 4;
+    if (precision == FPC_PREC_FP32) return kPackedF32ReplicaBytes * kWeightReplicas;
     if (precision == FPC_PREC_BF16) return packed_bf16_bytes();
     return 0;
 }
@@ -284,9 +285,9 @@ int fpc_pack_weights(const fpc_weights *w, int precision, void *d_packed, size_t
         return FPC_ERR_ARG;
     cudaStream_t st = (cudaStream_t)stream;
     if (precision == FPC_PREC_FP32) {
-        if (packed_bytes < (size_t)kPackedF32Floats * 4) return FPC_ERR_WORKSPACE;
+        if (packed_bytes < kPackedF32ReplicaBytes * kWeightReplicas) return FPC_ERR_WORKSPACE;
         int n = kStreamFloats + kBiasFloats + kFcFloats + kFc;
-        pack_weights_f32_kernel<<<(n + 255) / 256, 256, 0, st>>>(*w, (float *)d_packed);
+        pack_weights_f32_kernel<<<dim3((n + 255) / 256, kWeightReplicas), 256, 0, st>>>(*w, (float *)d_packed);
         FPC_LAUNCH_CHECK();
         return FPC_OK;
     }

@@ -74,6 +74,19 @@ __device__ __forceinline__ void dot2x2(const Cw2 &w, const float *__restrict__ x
     a01 = __fmaf_rn(tb, w.c0[16], a01); a11 = __fmaf_rn(tb, w.c1[16], a11);
 }
 
+// Gram rows of one vector pair (5 survivors each, the thread's two columns)
+struct GramBuf { float2 a[kSurv], c[kSurv]; };
+
+__device__ __forceinline__ void gram_load(GramBuf &g, const float *__restrict__ G, const int *__restrict__ surv, int va, int vc,
+                                          int Kp, int k)
+{
+#pragma unroll
+    for (int s2 = 0; s2 < kSurv; ++s2) {
+        g.a[s2] = *reinterpret_cast<const float2 *>(G + (size_t)surv[va * kSurv + s2] * Kp + k);
+        g.c[s2] = *reinterpret_cast<const float2 *>(G + (size_t)surv[vc * kSurv + s2] * Kp + k);
+    }
+}
+
 __device__ __forceinline__ unsigned screen_key(float v, unsigned k)
 {
     return (__float_as_uint(fmaxf(v, 0.0f)) & 0xfffffc00u) | k;
@@ -104,6 +117,14 @@ __device__ __forceinline__ void ins3(unsigned &t0, unsigned &t1, unsigned &t2, u
     t2 = min(t2, x);
 }
 
+__device__ __forceinline__ void ins4(unsigned &t0, unsigned &t1, unsigned &t2, unsigned &t3, unsigned x)
+{
+    unsigned lo = min(t0, x); x = max(t0, x); t0 = lo;
+    lo = min(t1, x); x = max(t1, x); t1 = lo;
+    lo = min(t2, x); x = max(t2, x); t2 = lo;
+    t3 = min(t3, x);
+}
+
 // top-2 of a stream of non-negative floats with the index of the smallest
 __device__ __forceinline__ void upd2(float &m1, int &i1, float &m2, float v, int idx)
 {
@@ -120,7 +141,7 @@ template <typename T>
 __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, const char *__restrict__ cbbase, const int *__restrict__ list,
                                         int n, int maxn, const float *__restrict__ rs, float *__restrict__ rq,
                                         int *__restrict__ idx1, int *__restrict__ idx2, char *__restrict__ scratch,
-                                        int scratch_bytes, int tid, T *__restrict__ qglobal = nullptr)
+                                        int scratch_bytes, int tid, T *__restrict__ qglobal = nullptr, long long *dbg = nullptr)
 {
     const int warp = tid >> 5, lane = tid & 31;
     // The header is re-read here on every call (volatile): its fields are loop-invariant for the
@@ -135,6 +156,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
     }
     const int Kp = bk.Kp;
     const bool two = bk.stages == 2;
+    long long tq0 = dbg ? clock64() : 0;
+#define FPC_VQT(i) do { if (dbg) { const long long t_ = clock64(); dbg[i] += t_ - tq0; tq0 = t_; } } while (0)
     int vb = (scratch_bytes - (int)screen_fixed_bytes(maxn)) / 4096;
     vb = (vb > 8 ? 8 : vb) & ~1;                       // vectors are processed in pairs
     unsigned *keybuf = reinterpret_cast<unsigned *>(scratch);
@@ -161,6 +184,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
         flag[tid] = 0;
     }
     named_bar_sync(1, kComputeThreads);
+    FPC_VQT(2);
 
     Cw2 w;
     if (two) {
@@ -189,28 +213,60 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 }
             }
             named_bar_sync(1, kComputeThreads);
+            FPC_VQT(3);
             if (warp < nb) {
                 const int v = base + warp;
-                unsigned t0 = 0xffffffffu, t1 = 0xffffffffu, t2 = 0xffffffffu;
+                unsigned t0 = 0xffffffffu, t1 = 0xffffffffu, t2 = 0xffffffffu, t3 = 0xffffffffu;
 #pragma unroll 2
                 for (int i = 0; i < 8; ++i) {
                     const uint4 kk = reinterpret_cast<const uint4 *>(keybuf + warp * 1024)[i * 32 + lane];
-                    ins3(t0, t1, t2, kk.x); ins3(t0, t1, t2, kk.y); ins3(t0, t1, t2, kk.z); ins3(t0, t1, t2, kk.w);
+                    ins4(t0, t1, t2, t3, kk.x); ins4(t0, t1, t2, t3, kk.y); ins4(t0, t1, t2, t3, kk.z); ins4(t0, t1, t2, t3, kk.w);
                 }
-                unsigned g[6];
+                unsigned g[8];
                 int popped = 0;
 #pragma unroll
-                for (int r = 0; r < 6; ++r) {
+                for (int r = 0; r < 8; ++r) {
                     const unsigned gm = __reduce_min_sync(0xffffffffu, t0);
                     g[r] = gm;
-                    if (t0 == gm) { t0 = t1; t1 = t2; t2 = 0xffffffffu; ++popped; }
+                    if (t0 == gm) { t0 = t1; t1 = t2; t2 = t3; t3 = 0xffffffffu; ++popped; }
                 }
-                // a lane that gave up all three of its keys may hide a fourth: undecidable here
-                const bool exhausted = __any_sync(0xffffffffu, popped >= 3);
+                // a lane that gave up all four of its keys may hide a fifth: undecidable here
+                const bool exhausted = __any_sync(0xffffffffu, popped >= 4);
                 const float M = marg[2 * v];
-                const float v5 = __uint_as_float(g[4] & 0xfffffc00u), v6 = __uint_as_float(g[5] & 0xfffffc00u);
+                const float v5 = __uint_as_float(g[4] & 0xfffffc00u);
                 const float thr = __fadd_ru(__fmaf_ru(v5, 4.8828125e-4f, v5), M);
-                const bool ok = !exhausted && (v6 > thr);      // NaN-safe: anything odd is flagged
+                // keys above thr are provably worse than the five smallest screened keys, so the exact top 5 is
+                // among the nc keys at or below it
+                int nc = 5;
+#pragma unroll
+                for (int r = 5; r < 8; ++r) nc += (__uint_as_float(g[r] & 0xfffffc00u) <= thr) ? 1 : 0;   // NaN-safe below
+                bool ok = !exhausted && (__uint_as_float(g[5] & 0xfffffc00u) > thr);
+                if (!ok && !exhausted && nc < 8) {      // g is sorted: the first key not counted in nc is above thr
+                    // near-tie around rank 5: decide among the nc candidates with the reference's exact arithmetic
+                    unsigned mine = g[0];
+#pragma unroll
+                    for (int r = 1; r < 8; ++r) mine = lane == r ? g[r] : mine;
+                    T d = Rn<T>::inf();
+                    int ki = 0x7fffffff;
+                    if (lane < nc) {
+                        ki = (int)(mine & 1023u);
+                        const T *crow = reinterpret_cast<const T *>(cbbase + bk.off_r[0]) + (size_t)ki * kDim;
+                        const float *xr = rs + list[v] * kLdR + 4;
+                        T xv[kDim], cv[kDim];
+#pragma unroll
+                        for (int dd = 0; dd < kDim; ++dd) { xv[dd] = (T)xr[dd]; cv[dd] = crow[dd]; }
+                        d = dist17<T>(xv, cv);
+                    }
+#pragma unroll
+                    for (int r = 0; r < kSurv; ++r) {
+                        T wd = d;
+                        int wi = ki;
+                        warp_argmin(wd, wi);
+                        g[r] = (unsigned)wi;                  // only the index part is used from here on
+                        if (ki == wi) { d = Rn<T>::inf(); ki = 0x7fffffff; }
+                    }
+                    ok = true;
+                }
                 if (lane < kSurv) {
                     const unsigned gl = lane == 0 ? g[0] : lane == 1 ? g[1] : lane == 2 ? g[2] : lane == 3 ? g[3] : g[4];
                     const int ks = ok ? (int)(gl & 1023u) : lane;          // flagged rows keep harmless indices
@@ -227,6 +283,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 if (lane == 0 && !ok) flag[v] = 1;
             }
             named_bar_sync(1, kComputeThreads);
+            FPC_VQT(4);
         }
     }
 
@@ -242,42 +299,52 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
             const int k = 2 * tid + 512 * h;
             const bool act = k < Kp;
             if (act) load_cw2(w, cf, nf, Kp, k);
-            for (int v = 0; v < n; v += 2) {
+            // Gram rows (2 vectors x 5 survivors, one float2 each) are fetched a whole vector pair ahead into
+            // the other of two register buffers (the loop handles two pairs per trip, so no copies are needed):
+            // an L2 round trip is several hundred cycles, the work on one pair about as long.
+            GramBuf gx, gy;
+#pragma unroll
+            for (int s2 = 0; s2 < kSurv; ++s2) {
+                gx.a[s2] = make_float2(0.0f, 0.0f); gx.c[s2] = gx.a[s2]; gy.a[s2] = gx.a[s2]; gy.c[s2] = gx.a[s2];
+            }
+            const bool ld = act && two;
+            if (ld) gram_load(gx, G, surv, 0, min(1, n - 1), Kp, k);
+            auto pair = [&](const GramBuf &g, int v) {
                 const int va = v, vc = min(v + 1, n - 1);
                 const float inf = __int_as_float(0x7f800000);
                 float ma1 = inf, ma2 = inf, mc1 = inf, mc2 = inf;
                 int ia = 0, ic = 0;
                 if (act) {
-                    // Gram rows one survivor ahead (L2 latency) instead of all five up front (registers)
-                    float2 ga = make_float2(0.0f, 0.0f), gc = ga;
-                    if (two) {
-                        ga = *reinterpret_cast<const float2 *>(G + (size_t)surv[va * kSurv] * Kp + k);
-                        gc = *reinterpret_cast<const float2 *>(G + (size_t)surv[vc * kSurv] * Kp + k);
-                    }
                     float a00, a10, a01, a11;
                     dot2x2(w, rs + list[va] * kLdR + 4, rs + list[vc] * kLdR + 4, a00, a10, a01, a11);
                     const float Ma = marg[2 * va], nxa = marg[2 * va + 1], Mc = marg[2 * vc], nxc = marg[2 * vc + 1];
-#pragma unroll 1
-                    for (int s2 = 0; s2 < ns; ++s2) {
-                        const float2 gga = ga, ggc = gc;
-                        if (two && s2 + 1 < ns) {
-                            ga = *reinterpret_cast<const float2 *>(G + (size_t)surv[va * kSurv + s2 + 1] * Kp + k);
-                            gc = *reinterpret_cast<const float2 *>(G + (size_t)surv[vc * kSurv + s2 + 1] * Kp + k);
+#pragma unroll
+                    for (int s2 = 0; s2 < kSurv; ++s2) {
+                        if (s2 < ns) {
+                            const float bsa = two ? (sval[va * kSurv + s2] + Ma) : nxa;
+                            const float bsc = two ? (sval[vc * kSurv + s2] + Mc) : nxc;
+                            const int ib = (s2 << 10) | k;
+                            upd2(ma1, ia, ma2, (a00 + bsa) + g.a[s2].x, ib);
+                            upd2(ma1, ia, ma2, (a10 + bsa) + g.a[s2].y, ib + 1);
+                            upd2(mc1, ic, mc2, (a01 + bsc) + g.c[s2].x, ib);
+                            upd2(mc1, ic, mc2, (a11 + bsc) + g.c[s2].y, ib + 1);
                         }
-                        const float bsa = two ? (sval[va * kSurv + s2] + Ma) : nxa;
-                        const float bsc = two ? (sval[vc * kSurv + s2] + Mc) : nxc;
-                        const int ib = (s2 << 10) | k;
-                        upd2(ma1, ia, ma2, (a00 + bsa) + gga.x, ib);
-                        upd2(ma1, ia, ma2, (a10 + bsa) + gga.y, ib + 1);
-                        upd2(mc1, ic, mc2, (a01 + bsc) + ggc.x, ib);
-                        upd2(mc1, ic, mc2, (a11 + bsc) + ggc.y, ib + 1);
                     }
                 }
                 warp_top2_store(ma1, ia, ma2, lane, &part[va * 16 + h * 8 + warp]);
                 if (v + 1 < n) warp_top2_store(mc1, ic, mc2, lane, &part[vc * 16 + h * 8 + warp]);
+            };
+            for (int v = 0; v < n; v += 4) {
+                if (ld && v + 2 < n) gram_load(gy, G, surv, v + 2, min(v + 3, n - 1), Kp, k);
+                pair(gx, v);
+                if (v + 2 < n) {
+                    if (ld && v + 4 < n) gram_load(gx, G, surv, v + 4, min(v + 5, n - 1), Kp, k);
+                    pair(gy, v + 2);
+                }
             }
         }
         named_bar_sync(1, kComputeThreads);
+        FPC_VQT(5);
         if (tid < n && !flag[tid]) {
             const int v = tid;
             float b = part[v * 16].v1, sec = part[v * 16].v2;
@@ -330,6 +397,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
 
     // ---- exact search for the undecided rows ----
     const int nflag = cnt[0];
+    FPC_VQT(6);
+    if (dbg) { dbg[0] += n; dbg[1] += nflag; }     // debug counters (rows searched, rows sent to the exact search)
     if (nflag > 0) {
         // the row list must survive the fallback, which reuses the scratch: keep it in registers
         int mine = tid < nflag ? flist[tid] : 0;
@@ -343,18 +412,20 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
         vbe = vbe > 8 ? 8 : vbe;
         for (int off = 0; off < nflag; off += sb)
             vq_search_rows<T>(bk, cbbase, keep + off, min(sb, nflag - off), sb, rs, rq, idx1, idx2, scratch, vbe, tid, qglobal);
+        FPC_VQT(7);
     }
+#undef FPC_VQT
 }
 
 // dtype dispatch used by the fused frame-step kernels
 __device__ __forceinline__ void vq_dispatch_screened(const PackedVq &bk, const char *cbbase, const int *list, int n, int maxn,
                                                      const float *rs, float *rq, int *idx1, int *idx2, char *scratch,
-                                                     int scratch_bytes, int tid)
+                                                     int scratch_bytes, int tid, long long *dbg = nullptr)
 {
     if (bk.dtype == FPC_F32)
-        vq_search_rows_screened<float>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid);
+        vq_search_rows_screened<float>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
     else
-        vq_search_rows_screened<double>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid);
+        vq_search_rows_screened<double>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
 }
 
 }  // namespace fpc

@@ -201,6 +201,11 @@ int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, d
  * self-test of the tensor-core plumbing (tcgen05.mma / TMEM) the bf16 predictor is built on:
  * d_out (128,N) f32 = A (128,K) bf16 x B (N,K) bf16 ^T.  16 <= N <= 256, N % 16 == 0, K % 16 == 0.
  * ------------------------------------------------------------------------------------------- */
+/* debug aid: d_buf = 8 int64 counters in device memory (zeroed by the caller) or NULL to switch off;
+ * CTA 0 of fpc_encode (fp32) adds the SM cycles it spent in [GRU, FC, thresholds+scalar, VQ, feedback] and the
+ * number of frames.  Used by tools/phase_profile.py; not part of the reference-facing surface. */
+int fpc_debug_set_phase_buffer(void *d_buf);
+
 int fpc_selftest_umma(const void *d_a_bf16, const void *d_b_bf16, int N, int K, float *d_out, void *stream);
 
 #if defined(__GNUC__)

@@ -1,0 +1,37 @@
+#!/usr/bin/env python
+"""Per-phase cycle breakdown of the fp32 frame-step kernel (CTA 0), via fpc_debug_set_phase_buffer.
+    python tools/phase_profile.py [utts] [frames] [l1 l2]"""
+import os, sys, tempfile
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+sys.path.insert(0, os.path.join(ROOT, "feature-predictor-for-speech-codec_b200"))
+import numpy as np, torch
+import fpc_native as N, fpc_synth as S
+from models.wavernn import Wavernn
+U = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
+L = int(sys.argv[2]) if len(sys.argv) > 2 else 200
+l1, l2 = (float(sys.argv[3]), float(sys.argv[4])) if len(sys.argv) > 4 else (0.09, 0.28)
+m = Wavernn(20, 384, 128, 18).eval(); m.load_state_dict(S.make_state_dict(0)); m = m.cuda()
+d = tempfile.mkdtemp(); cfg = S.save_codebooks(S.make_codebooks(0), d)
+base = S.make_features(min(U, 256), L)
+feat = torch.from_numpy(np.tile(base, ((U + len(base) - 1) // len(base), 1, 1))[:U]).cuda()
+buf = torch.zeros(16 * 148, dtype=torch.int64, device="cuda")
+with torch.no_grad():
+    m.encode_device(cfg, feat, None, l1, l2); torch.cuda.synchronize()
+    N.lib().fpc_debug_set_phase_buffer(buf.data_ptr())
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record(); res = m.encode_device(cfg, feat, None, l1, l2); e1.record(); torch.cuda.synchronize()
+    N.lib().fpc_debug_set_phase_buffer(None)
+c = buf.cpu().numpy().astype(np.float64).reshape(148, 16)
+c = c[c[:, 5] > 0]
+fr = c[:, 5:6]
+names = ["gru", "fc+residual", "thresholds+scalar", "vq", "feedback/out"]
+per = c[:, :5] / fr
+tot = per.sum(1)
+print("kernel %.2f ms for %d x %d frames (%.2f M frames/s); %d CTAs; cycles/frame min %.0f mean %.0f max %.0f" % (
+    e0.elapsed_time(e1), U, L, U * L / e0.elapsed_time(e1) / 1e3, len(c), tot.min(), tot.mean(), tot.max()))
+for i, n_ in enumerate(names):
+    print("  %-18s min %8.0f  mean %8.0f  max %8.0f   %5.1f%% of mean" % (n_, per[:, i].min(), per[:, i].mean(), per[:, i].max(), 100 * per[:, i].mean() / tot.mean()))
+print("vq rows %d, sent to the exact search %d (%.2f %%)" % (c[:, 6].sum(), c[:, 7].sum(), 100 * c[:, 7].sum() / max(c[:, 6].sum(), 1)))
+for i, n_ in enumerate(["margins", "stage-0 screen", "stage-0 select", "last-stage screen", "merge+gather", "exact fallback"]):
+    print("     vq/%-18s mean %8.0f cycles/frame" % (n_, (c[:, 8 + i] / fr[:, 0]).mean()))
+print("above-threshold fractions: c0 %.3f  c1..17 %.3f" % (res.ind1.mean().item(), res.ind2.mean().item()))

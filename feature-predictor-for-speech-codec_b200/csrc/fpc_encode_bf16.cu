@@ -306,6 +306,9 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
         if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
     }
     uint32_t n_full = 0;
+    const bool prof = P.prof != nullptr && tid == 0;
+    long long pt[kPhCount] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
+#define FPC_PHASE(ph) do { if (prof) { const long long t_ = clock64(); pt[ph] += t_ - pt0; pt0 = t_; } } while (0)
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int b0 = tile * NU;
@@ -331,6 +334,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     else featv[e2] = j < kFc ? __ldg(P.rq_in + fo * kFc + j) : __ldg(P.pitch_in + fo * 2 + (j - kFc));
                 }
             }
+            if (prof) pt0 = clock64();
             // ---- GRU 1 (wavernn.py:71): gate epilogues of the three passes ----
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
@@ -354,6 +358,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             if (lane == 0) mbar_arrive(acc_empty);
             named_bar_sync(1, kComputeThreads);
 
+            FPC_PHASE(kPhGru);
             // ---- relu, dual_fc, 2*tanh (wavernn.py:87-92); residual (:196) ----
 #pragma unroll
             for (int e2 = 0; e2 < NE; ++e2) {
@@ -385,6 +390,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                 for (int i = tid; i < NU * 20; i += kComputeThreads) rq[i] = 0.0f;
                 named_bar_sync(1, kComputeThreads);
 
+                FPC_PHASE(kPhFc);
                 // ---- indicators (:201-212) and the scalar quantiser for c0 (:217-225) ----
                 for (int u = warp; u < NU; u += 8) {
                     const bool valid = b0 + u < P.B;
@@ -426,6 +432,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                 }
                 named_bar_sync(1, kComputeThreads);
 
+                FPC_PHASE(kPhScalar);
                 if (P.mode == kModeQuantize) {
                     // ---- VQ for c1..c17 (:228-240): rows compacted by branch ----
                     if (warp == 0) {
@@ -455,13 +462,14 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                         const int nrows = book ? nB : nA;
                         if (nrows > 0)
                             vq_dispatch_screened(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, NU, rs, rq, idx1s, idx2s,
-                                                 scratch, S::kScratchBytes, tid);
+                                                 scratch, S::kScratchBytes, tid, prof ? pt + kPhVqDbg : nullptr);
                     }
                 }
             } else {
                 named_bar_sync(1, kComputeThreads);
             }
 
+            FPC_PHASE(kPhVq);
             // ---- feedback (:242 / :252), outputs, next input frame (bf16 B-operand tile) ----
             unsigned char *xn = x1[cur ^ 1];
 #pragma unroll
@@ -521,9 +529,14 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             umma::fence_async_smem();
             named_bar_sync(1, kComputeThreads);
             if (lane == 0 && fr + 1 < P.L) mbar_arrive(act_ready);
+            FPC_PHASE(kPhOut);
+            if (prof) pt[kPhFrames] += 1;
             cur ^= 1;
         }
     }
+    if (prof)
+        for (int i = 0; i < kPhCount; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof) + (size_t)blockIdx.x * kPhCount + i, (unsigned long long)pt[i]);
+#undef FPC_PHASE
     named_bar_sync(1, kComputeThreads);
     if (warp == 0) umma::tmem_dealloc(tb, 4 * NU);
 }

@@ -32,8 +32,9 @@ namespace fpc {
 struct ScreenPart { float v1; int i1; float v2; int pad; };
 
 // scratch: keybuf u32[vb][1024] | surv int[maxn][5] | sval float[maxn][5] | marg float[maxn][2] |
-//          part ScreenPart[maxn][16] | flag int[maxn] | flist int[maxn] | cnt int[4]
-__host__ __device__ constexpr size_t screen_fixed_bytes(int maxn) { return (size_t)maxn * 312 + 16; }
+//          part ScreenPart[maxn][16] | flag int[maxn] | flist int[maxn] | xm2 float[maxn][20] (-2 x, 16-byte rows) |
+//          goff int[maxn][5] (Gram row offsets) | cnt int[4]
+__host__ __device__ constexpr size_t screen_fixed_bytes(int maxn) { return (size_t)maxn * 416 + 16; }
 
 // Register blocking of the dot products: a thread holds TWO codewords (34 + 2 registers) and streams
 // TWO vectors from shared memory against them -- four independent FMA chains, half the registers of a
@@ -51,7 +52,7 @@ __device__ __forceinline__ void load_cw2(Cw2 &w, const float *__restrict__ cf, c
     w.n0 = t.x; w.n1 = t.y;
 }
 
-// a[cw][vec] = ||c_cw||^2 - 2 <x_vec, c_cw>
+// a[cw][vec] = ||c_cw||^2 + <xm_vec, c_cw>, with xm = -2 x prepared once per vector in shared memory
 __device__ __forceinline__ void dot2x2(const Cw2 &w, const float *__restrict__ xa, const float *__restrict__ xb, float &a00,
                                        float &a10, float &a01, float &a11)
 {
@@ -60,8 +61,8 @@ __device__ __forceinline__ void dot2x2(const Cw2 &w, const float *__restrict__ x
     for (int d4 = 0; d4 < 4; ++d4) {
         const float4 pa = *reinterpret_cast<const float4 *>(xa + 4 * d4);
         const float4 pb = *reinterpret_cast<const float4 *>(xb + 4 * d4);
-        const float ea[4] = {-2.0f * pa.x, -2.0f * pa.y, -2.0f * pa.z, -2.0f * pa.w};
-        const float eb[4] = {-2.0f * pb.x, -2.0f * pb.y, -2.0f * pb.z, -2.0f * pb.w};
+        const float ea[4] = {pa.x, pa.y, pa.z, pa.w};
+        const float eb[4] = {pb.x, pb.y, pb.z, pb.w};
 #pragma unroll
         for (int e = 0; e < 4; ++e) {
             const int d = 4 * d4 + e;
@@ -69,7 +70,7 @@ __device__ __forceinline__ void dot2x2(const Cw2 &w, const float *__restrict__ x
             a01 = __fmaf_rn(eb[e], w.c0[d], a01); a11 = __fmaf_rn(eb[e], w.c1[d], a11);
         }
     }
-    const float ta = -2.0f * xa[16], tb = -2.0f * xb[16];
+    const float ta = xa[16], tb = xb[16];
     a00 = __fmaf_rn(ta, w.c0[16], a00); a10 = __fmaf_rn(ta, w.c1[16], a10);
     a01 = __fmaf_rn(tb, w.c0[16], a01); a11 = __fmaf_rn(tb, w.c1[16], a11);
 }
@@ -77,13 +78,13 @@ __device__ __forceinline__ void dot2x2(const Cw2 &w, const float *__restrict__ x
 // Gram rows of one vector pair (5 survivors each, the thread's two columns)
 struct GramBuf { float2 a[kSurv], c[kSurv]; };
 
-__device__ __forceinline__ void gram_load(GramBuf &g, const float *__restrict__ G, const int *__restrict__ surv, int va, int vc,
-                                          int Kp, int k)
+__device__ __forceinline__ void gram_load(GramBuf &g, const float *__restrict__ Gk /* G + this thread's column */,
+                                          const int *__restrict__ goff, int va, int vc)
 {
 #pragma unroll
     for (int s2 = 0; s2 < kSurv; ++s2) {
-        g.a[s2] = *reinterpret_cast<const float2 *>(G + (size_t)surv[va * kSurv + s2] * Kp + k);
-        g.c[s2] = *reinterpret_cast<const float2 *>(G + (size_t)surv[vc * kSurv + s2] * Kp + k);
+        g.a[s2] = *reinterpret_cast<const float2 *>(Gk + goff[va * kSurv + s2]);
+        g.c[s2] = *reinterpret_cast<const float2 *>(Gk + goff[vc * kSurv + s2]);
     }
 }
 
@@ -167,7 +168,9 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
     ScreenPart *part = reinterpret_cast<ScreenPart *>(marg + maxn * 2);
     int *flag = reinterpret_cast<int *>(part + maxn * 16);
     int *flist = flag + maxn;
-    int *cnt = flist + maxn;
+    float *xm2 = reinterpret_cast<float *>(flist + maxn);     // 16-byte aligned: every block above is a multiple of 16 per row
+    int *goff = reinterpret_cast<int *>(xm2 + maxn * 20);
+    int *cnt = goff + maxn * 5;
     const float *cmax = reinterpret_cast<const float *>(cbbase + bk.off_cmax);
 
     // ---- per-vector constants: margin M and the offset nx that makes screened values positive ----
@@ -182,6 +185,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
         marg[2 * tid] = M;
         marg[2 * tid + 1] = __fadd_ru(n2, M);
         flag[tid] = 0;
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) xm2[tid * 20 + d] = -2.0f * xr[d];      // exact (power of two)
     }
     named_bar_sync(1, kComputeThreads);
     FPC_VQT(2);
@@ -203,7 +208,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                     uint2 ka = make_uint2(0xffffffffu, 0xffffffffu), kc = ka;
                     if (act) {
                         float a00, a10, a01, a11;
-                        dot2x2(w, rs + list[va] * kLdR + 4, rs + list[vc] * kLdR + 4, a00, a10, a01, a11);
+                        dot2x2(w, xm2 + va * 20, xm2 + vc * 20, a00, a10, a01, a11);
                         const float nxa = marg[2 * va + 1], nxc = marg[2 * vc + 1];
                         ka.x = screen_key(a00 + nxa, (unsigned)k); ka.y = screen_key(a10 + nxa, (unsigned)k + 1);
                         kc.x = screen_key(a01 + nxc, (unsigned)k); kc.y = screen_key(a11 + nxc, (unsigned)k + 1);
@@ -271,6 +276,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                     const unsigned gl = lane == 0 ? g[0] : lane == 1 ? g[1] : lane == 2 ? g[2] : lane == 3 ? g[3] : g[4];
                     const int ks = ok ? (int)(gl & 1023u) : lane;          // flagged rows keep harmless indices
                     surv[v * kSurv + lane] = ks;
+                    goff[v * kSurv + lane] = ks * Kp;
                     // full-precision screened value of the survivor (||x - c0||^2 up to the common offset);
                     // (float)c of the row-major copy is the shadow value, and the row is contiguous
                     float a = nf[ks];
@@ -308,7 +314,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 gx.a[s2] = make_float2(0.0f, 0.0f); gx.c[s2] = gx.a[s2]; gy.a[s2] = gx.a[s2]; gy.c[s2] = gx.a[s2];
             }
             const bool ld = act && two;
-            if (ld) gram_load(gx, G, surv, 0, min(1, n - 1), Kp, k);
+            const float *Gk = G + k;
+            if (ld) gram_load(gx, Gk, goff, 0, min(1, n - 1));
             auto pair = [&](const GramBuf &g, int v) {
                 const int va = v, vc = min(v + 1, n - 1);
                 const float inf = __int_as_float(0x7f800000);
@@ -316,7 +323,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 int ia = 0, ic = 0;
                 if (act) {
                     float a00, a10, a01, a11;
-                    dot2x2(w, rs + list[va] * kLdR + 4, rs + list[vc] * kLdR + 4, a00, a10, a01, a11);
+                    dot2x2(w, xm2 + va * 20, xm2 + vc * 20, a00, a10, a01, a11);
                     const float Ma = marg[2 * va], nxa = marg[2 * va + 1], Mc = marg[2 * vc], nxc = marg[2 * vc + 1];
 #pragma unroll
                     for (int s2 = 0; s2 < kSurv; ++s2) {
@@ -335,10 +342,10 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 if (v + 1 < n) warp_top2_store(mc1, ic, mc2, lane, &part[vc * 16 + h * 8 + warp]);
             };
             for (int v = 0; v < n; v += 4) {
-                if (ld && v + 2 < n) gram_load(gy, G, surv, v + 2, min(v + 3, n - 1), Kp, k);
+                if (ld && v + 2 < n) gram_load(gy, Gk, goff, v + 2, min(v + 3, n - 1));
                 pair(gx, v);
                 if (v + 2 < n) {
-                    if (ld && v + 4 < n) gram_load(gx, G, surv, v + 4, min(v + 5, n - 1), Kp, k);
+                    if (ld && v + 4 < n) gram_load(gx, Gk, goff, v + 4, min(v + 5, n - 1));
                     pair(gy, v + 2);
                 }
             }

@@ -1,6 +1,6 @@
 #!/usr/bin/env python
-"""Per-phase cycle breakdown of the fp32 frame-step kernel (CTA 0), via fpc_debug_set_phase_buffer.
-    python tools/phase_profile.py [utts] [frames] [l1 l2]"""
+"""Per-phase cycle breakdown of the frame-step kernels (all CTAs), via fpc_debug_set_phase_buffer.
+    python tools/phase_profile.py [utts] [frames] [l1 l2] [bf16]"""
 import os, sys, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "feature-predictor-for-speech-codec_b200"))
@@ -10,7 +10,10 @@ from models.wavernn import Wavernn
 U = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 l1, l2 = (float(sys.argv[3]), float(sys.argv[4])) if len(sys.argv) > 4 else (0.09, 0.28)
+bf16 = len(sys.argv) > 5 and sys.argv[5] == "bf16"
 m = Wavernn(20, 384, 128, 18).eval(); m.load_state_dict(S.make_state_dict(0)); m = m.cuda()
+if bf16:
+    m.precision = N.FPC_PREC_BF16
 d = tempfile.mkdtemp(); cfg = S.save_codebooks(S.make_codebooks(0), d)
 base = S.make_features(min(U, 256), L)
 feat = torch.from_numpy(np.tile(base, ((U + len(base) - 1) // len(base), 1, 1))[:U]).cuda()

@@ -40,17 +40,21 @@ constexpr int kFc = FPC_FC;            // 18
 constexpr int kDim = FPC_CODE_DIMS;    // 17
 constexpr int kSurv = FPC_SURVIVORS;   // 5
 
-// fp32 weight stream: "groups" of 4 consecutive k for 384 gate columns of one pass
-// (128 hidden units x {r,z,n}); group = [6 column slots][64 unit pairs][4 k] floats.
-constexpr int kGroupFloats = 6 * 64 * 4;                 // 1536
-constexpr int kGroupBytes = kGroupFloats * 4;            // 6144
-constexpr int kG1x = kIn / 4;                            // 5 groups: GRU1 input part
-constexpr int kG1h = kH1 / 4;                            // 96 groups: GRU1 hidden part
-constexpr int kG1 = kG1x + kG1h;                         // 101 per pass, 3 passes
-constexpr int kG2x = kH1 / 4;                            // 96: GRU2 input part (h1')
-constexpr int kG2h = kH2 / 4;                            // 32: GRU2 hidden part
-constexpr int kG2 = kG2x + kG2h;                         // 128
-constexpr int kGroupsPerFrame = 3 * kG1 + kG2;           // 431
+// fp32 weight stream: "groups" of kGk consecutive k for the 384 gate columns of one pass
+// (128 hidden units x {r,z,n}); group = [6 column slots][kGk/4 quads][64 unit pairs][4 k] floats, so a warp reads
+// 128 contiguous bytes per (slot, quad).  kGk = 8 halves the per-group hand-off cost (mbarrier wait, LDS latency
+// exposed at the group boundary) relative to 4; the x part of GRU 1 is padded from 20 to 24 inputs with zero
+// weights (fma(0, 0, acc) leaves the canonical chain's value unchanged).
+constexpr int kGk = 8;
+constexpr int kGroupFloats = 6 * 64 * kGk;               // 3072
+constexpr int kGroupBytes = kGroupFloats * 4;            // 12288
+constexpr int kG1x = (kIn + kGk - 1) / kGk;              // 3 groups: GRU1 input part (20 -> 24)
+constexpr int kG1h = kH1 / kGk;                          // 48 groups: GRU1 hidden part
+constexpr int kG1 = kG1x + kG1h;                         // 51 per pass, 3 passes
+constexpr int kG2x = kH1 / kGk;                          // 48: GRU2 input part (h1')
+constexpr int kG2h = kH2 / kGk;                          // 16: GRU2 hidden part
+constexpr int kG2 = kG2x + kG2h;                         // 64
+constexpr int kGroupsPerFrame = 3 * kG1 + kG2;           // 217
 constexpr int kStreamFloats = kGroupsPerFrame * kGroupFloats;
 constexpr int kBiasFloats = 4 * 4 * 128;                 // [3 GRU1 passes + GRU2][br,bz,bni,bnh][128]
 constexpr int kFcFloats = kFc * kH2;                     // 2304

@@ -29,7 +29,7 @@
 
 namespace fpc {
 
-constexpr int kStages = 8;             // weight ring depth
+constexpr int kStages = 4;             // weight ring depth
 constexpr int kThreads = kComputeThreads + 128;   // 2 compute warpgroups + 1 producer warpgroup
 constexpr int kLd1 = kH1 + 4;          // 388: padded row strides (floats) -> conflict-free float4 rows
 constexpr int kLd2 = kH2 + 4;          // 132
@@ -76,23 +76,29 @@ __device__ __forceinline__ void gemm_part(float (&ar)[TU][2], float (&az)[TU][2]
                                           const float *__restrict__ arow, int lda, const float4 *__restrict__ ring,
                                           uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
 {
+    constexpr int NQ = kGk / 4;
     for (int g = 0; g < ng; ++g) {
         mbar_wait(&full[pp.s], pp.ph);
         const float4 *sw = ring + pp.s * (kGroupFloats / 4) + ug;
-        float4 w[6];
+        float4 w[6][NQ];
 #pragma unroll
-        for (int c = 0; c < 6; ++c) w[c] = sw[c * 64];
+        for (int c = 0; c < 6; ++c)
+#pragma unroll
+            for (int q = 0; q < NQ; ++q) w[c][q] = sw[(c * NQ + q) * 64];
 #pragma unroll
         for (int i = 0; i < TU; ++i) {
-            const float4 a = *reinterpret_cast<const float4 *>(arow + (size_t)(4 * i) * lda + 4 * g);
 #pragma unroll
-            for (int e = 0; e < 2; ++e) {
-                float r = ar[i][e], z = az[i][e], n = an[i][e];
-                r = __fmaf_rn(w[0 + e].x, a.x, r); z = __fmaf_rn(w[2 + e].x, a.x, z); n = __fmaf_rn(w[4 + e].x, a.x, n);
-                r = __fmaf_rn(w[0 + e].y, a.y, r); z = __fmaf_rn(w[2 + e].y, a.y, z); n = __fmaf_rn(w[4 + e].y, a.y, n);
-                r = __fmaf_rn(w[0 + e].z, a.z, r); z = __fmaf_rn(w[2 + e].z, a.z, z); n = __fmaf_rn(w[4 + e].z, a.z, n);
-                r = __fmaf_rn(w[0 + e].w, a.w, r); z = __fmaf_rn(w[2 + e].w, a.w, z); n = __fmaf_rn(w[4 + e].w, a.w, n);
-                ar[i][e] = r; az[i][e] = z; an[i][e] = n;
+            for (int q = 0; q < NQ; ++q) {
+                const float4 a = *reinterpret_cast<const float4 *>(arow + (size_t)(4 * i) * lda + kGk * g + 4 * q);
+#pragma unroll
+                for (int e = 0; e < 2; ++e) {
+                    float r = ar[i][e], z = az[i][e], n = an[i][e];
+                    r = __fmaf_rn(w[0 + e][q].x, a.x, r); z = __fmaf_rn(w[2 + e][q].x, a.x, z); n = __fmaf_rn(w[4 + e][q].x, a.x, n);
+                    r = __fmaf_rn(w[0 + e][q].y, a.y, r); z = __fmaf_rn(w[2 + e][q].y, a.y, z); n = __fmaf_rn(w[4 + e][q].y, a.y, n);
+                    r = __fmaf_rn(w[0 + e][q].z, a.z, r); z = __fmaf_rn(w[2 + e][q].z, a.z, z); n = __fmaf_rn(w[4 + e][q].z, a.z, n);
+                    r = __fmaf_rn(w[0 + e][q].w, a.w, r); z = __fmaf_rn(w[2 + e][q].w, a.w, z); n = __fmaf_rn(w[4 + e][q].w, a.w, n);
+                    ar[i][e] = r; az[i][e] = z; an[i][e] = n;
+                }
             }
         }
         __syncwarp();

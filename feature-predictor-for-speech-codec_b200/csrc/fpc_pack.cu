@@ -12,8 +12,8 @@ unsigned long long g_launch_count = 0;
 
 // ------------------------------------------------------------------------------------------
 // fp32 weight stream.  One thread per destination float.
-//   group g of a pass -> [slot c = gate*2 + e][unit pair ug 0..63][kk 0..3]
-//   hidden unit j = pass*128 + 2*ug + e ; k = 4*(group index within part) + kk
+//   group g of a pass -> [slot c = gate*2 + e][quad q][unit pair ug 0..63][4 k]
+//   hidden unit j = pass*128 + 2*ug + e ; k = kGk*(group index within part) + 4*q + kk
 // ------------------------------------------------------------------------------------------
 __global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out0)
 {
@@ -22,21 +22,27 @@ __global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out0)
     if (t < kStreamFloats) {
         int g = t / kGroupFloats;
         int r = t - g * kGroupFloats;
-        int c = r / 256, ug = (r >> 2) & 63, kk = r & 3;
+        // [slot c][quad q][unit pair ug][4 k]
+        int c = r / (kGk * 64), r2 = r - c * (kGk * 64);
+        int q = r2 / 256, ug = (r2 >> 2) & 63, kk = 4 * q + (r2 & 3);
         int gate = c >> 1, e = c & 1;
-        float v;
+        float v = 0.0f;
         if (g < 3 * kG1) {
             int pass = g / kG1, gi = g - pass * kG1;
             int j = pass * 128 + 2 * ug + e;
             int row = gate * kH1 + j;
-            if (gi < kG1x) v = w.w_ih1[(size_t)row * kIn + 4 * gi + kk];
-            else v = w.w_hh1[(size_t)row * kH1 + 4 * (gi - kG1x) + kk];
+            if (gi < kG1x) {
+                int k = kGk * gi + kk;
+                if (k < kIn) v = w.w_ih1[(size_t)row * kIn + k];
+            } else {
+                v = w.w_hh1[(size_t)row * kH1 + kGk * (gi - kG1x) + kk];
+            }
         } else {
             int gi = g - 3 * kG1;
             int j = 2 * ug + e;
             int row = gate * kH2 + j;
-            if (gi < kG2x) v = w.w_ih2[(size_t)row * kH1 + 4 * gi + kk];
-            else v = w.w_hh2[(size_t)row * kH2 + 4 * (gi - kG2x) + kk];
+            if (gi < kG2x) v = w.w_ih2[(size_t)row * kH1 + kGk * gi + kk];
+            else v = w.w_hh2[(size_t)row * kH2 + kGk * (gi - kG2x) + kk];
         }
         out[t] = v;
         return;

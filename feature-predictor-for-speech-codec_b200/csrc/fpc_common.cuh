@@ -41,8 +41,9 @@ constexpr int kDim = FPC_CODE_DIMS;    // 17
 constexpr int kSurv = FPC_SURVIVORS;   // 5
 
 // fp32 weight stream: "groups" of kGk consecutive k for the 384 gate columns of one pass
-// (128 hidden units x {r,z,n}); group = [6 column slots][kGk/4 quads][64 unit pairs][4 k] floats, so a warp reads
-// 128 contiguous bytes per (slot, quad).  kGk = 8 halves the per-group hand-off cost (mbarrier wait, LDS latency
+// (128 hidden units x {r,z,n}); group = [3 gates][kGk/2 k-pairs][64 unit pairs][(e0,k) (e1,k) (e0,k+1) (e1,k+1)]
+// floats: a warp reads 128 contiguous bytes per (gate, k-pair), and the two hidden units of a thread sit in one
+// 64-bit register pair -- the operand form of the packed fma.rn.f32x2 (SASS FFMA2) the gate GEMM issues.  kGk = 8 halves the per-group hand-off cost (mbarrier wait, LDS latency
 // exposed at the group boundary) relative to 4; the x part of GRU 1 is padded from 20 to 24 inputs with zero
 // weights (fma(0, 0, acc) leaves the canonical chain's value unchanged).
 constexpr int kGk = 8;

@@ -71,34 +71,55 @@ struct Pipe {
 // buffer, barrier probed two groups ahead -- measured 20-25 % SLOWER on B200 than this plain loop:
 // 392 k vs 316 k cycles per frame for the GRU stage; ptxas schedules the simple form better.)
 // ------------------------------------------------------------------------------------------
+// packed fp32 FMA on a register pair: d.x = fma(a.x, b, c.x), d.y = fma(a.y, b, c.y), each lane IEEE round-to-nearest
+// (PTX fma.rn.f32x2, SASS FFMA2 with the scalar-broadcast operand form).  Half the issue slots of two FFMAs and the
+// 64-bit operands straddle both register banks.
+__device__ __forceinline__ float2 fma2(float2 a, float b, float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
 template <int TU>
-__device__ __forceinline__ void gemm_part(float (&ar)[TU][2], float (&az)[TU][2], float (&an)[TU][2], int ng,
+__device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], float2 (&an)[TU], int ng,
                                           const float *__restrict__ arow, int lda, const float4 *__restrict__ ring,
                                           uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
 {
-    constexpr int NQ = kGk / 4;
+    constexpr int NP = kGk / 2;      // k-pairs per group
     for (int g = 0; g < ng; ++g) {
         mbar_wait(&full[pp.s], pp.ph);
         const float4 *sw = ring + pp.s * (kGroupFloats / 4) + ug;
-        float4 w[6][NQ];
+        float4 w[3][NP];             // [gate][k-pair] = (e0,k) (e1,k) (e0,k+1) (e1,k+1)
 #pragma unroll
-        for (int c = 0; c < 6; ++c)
+        for (int c = 0; c < 3; ++c)
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) w[c][q] = sw[(c * NQ + q) * 64];
+            for (int q = 0; q < NP; ++q) w[c][q] = sw[(c * NP + q) * 64];
 #pragma unroll
         for (int i = 0; i < TU; ++i) {
 #pragma unroll
-            for (int q = 0; q < NQ; ++q) {
+            for (int q = 0; q < kGk / 4; ++q) {
                 const float4 a = *reinterpret_cast<const float4 *>(arow + (size_t)(4 * i) * lda + kGk * g + 4 * q);
-#pragma unroll
-                for (int e = 0; e < 2; ++e) {
-                    float r = ar[i][e], z = az[i][e], n = an[i][e];
-                    r = __fmaf_rn(w[0 + e][q].x, a.x, r); z = __fmaf_rn(w[2 + e][q].x, a.x, z); n = __fmaf_rn(w[4 + e][q].x, a.x, n);
-                    r = __fmaf_rn(w[0 + e][q].y, a.y, r); z = __fmaf_rn(w[2 + e][q].y, a.y, z); n = __fmaf_rn(w[4 + e][q].y, a.y, n);
-                    r = __fmaf_rn(w[0 + e][q].z, a.z, r); z = __fmaf_rn(w[2 + e][q].z, a.z, z); n = __fmaf_rn(w[4 + e][q].z, a.z, n);
-                    r = __fmaf_rn(w[0 + e][q].w, a.w, r); z = __fmaf_rn(w[2 + e][q].w, a.w, z); n = __fmaf_rn(w[4 + e][q].w, a.w, n);
-                    ar[i][e] = r; az[i][e] = z; an[i][e] = n;
-                }
+                float2 r = ar[i], z = az[i], n = an[i];
+                // ascending k: the canonical chain of every accumulator
+                r = fma2(make_float2(w[0][2 * q].x, w[0][2 * q].y), a.x, r);
+                z = fma2(make_float2(w[1][2 * q].x, w[1][2 * q].y), a.x, z);
+                n = fma2(make_float2(w[2][2 * q].x, w[2][2 * q].y), a.x, n);
+                r = fma2(make_float2(w[0][2 * q].z, w[0][2 * q].w), a.y, r);
+                z = fma2(make_float2(w[1][2 * q].z, w[1][2 * q].w), a.y, z);
+                n = fma2(make_float2(w[2][2 * q].z, w[2][2 * q].w), a.y, n);
+                r = fma2(make_float2(w[0][2 * q + 1].x, w[0][2 * q + 1].y), a.z, r);
+                z = fma2(make_float2(w[1][2 * q + 1].x, w[1][2 * q + 1].y), a.z, z);
+                n = fma2(make_float2(w[2][2 * q + 1].x, w[2][2 * q + 1].y), a.z, n);
+                r = fma2(make_float2(w[0][2 * q + 1].z, w[0][2 * q + 1].w), a.w, r);
+                z = fma2(make_float2(w[1][2 * q + 1].z, w[1][2 * q + 1].w), a.w, z);
+                n = fma2(make_float2(w[2][2 * q + 1].z, w[2][2 * q + 1].w), a.w, n);
+                ar[i] = r; az[i] = z; an[i] = n;
             }
         }
         __syncwarp();
@@ -115,26 +136,21 @@ __device__ __forceinline__ void gru_pass(int ngx, int ngh, const float *__restri
                                          const float4 *__restrict__ ring, uint64_t *full, uint64_t *empty, Pipe &pp,
                                          int ug, int lane)
 {
-    float ar[TU][2], az[TU][2], ani[TU][2], anh[TU][2];
+    float2 ar[TU], az[TU], ani[TU], anh[TU];
     const float2 br = *reinterpret_cast<const float2 *>(bias + 0 * 128 + 2 * ug);
     const float2 bz = *reinterpret_cast<const float2 *>(bias + 1 * 128 + 2 * ug);
     const float2 bi = *reinterpret_cast<const float2 *>(bias + 2 * 128 + 2 * ug);
     const float2 bh = *reinterpret_cast<const float2 *>(bias + 3 * 128 + 2 * ug);
 #pragma unroll
-    for (int i = 0; i < TU; ++i) {
-        ar[i][0] = br.x; ar[i][1] = br.y;
-        az[i][0] = bz.x; az[i][1] = bz.y;
-        ani[i][0] = bi.x; ani[i][1] = bi.y;
-        anh[i][0] = bh.x; anh[i][1] = bh.y;
-    }
+    for (int i = 0; i < TU; ++i) { ar[i] = br; az[i] = bz; ani[i] = bi; anh[i] = bh; }
     gemm_part<TU>(ar, az, ani, ngx, xrow, ldx, ring, full, empty, pp, ug, lane);
     gemm_part<TU>(ar, az, anh, ngh, hrow, ldh, ring, full, empty, pp, ug, lane);
 #pragma unroll
     for (int i = 0; i < TU; ++i) {
         const float2 ho = *reinterpret_cast<const float2 *>(hold + (size_t)(4 * i) * ldo);
         float2 hn;
-        hn.x = gru_update(ar[i][0], az[i][0], ani[i][0], anh[i][0], ho.x);
-        hn.y = gru_update(ar[i][1], az[i][1], ani[i][1], anh[i][1], ho.y);
+        hn.x = gru_update(ar[i].x, az[i].x, ani[i].x, anh[i].x, ho.x);
+        hn.y = gru_update(ar[i].y, az[i].y, ani[i].y, anh[i].y, ho.y);
         *reinterpret_cast<float2 *>(hnew + (size_t)(4 * i) * ldo) = hn;
     }
 }

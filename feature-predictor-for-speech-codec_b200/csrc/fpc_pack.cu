@@ -12,8 +12,8 @@ unsigned long long g_launch_count = 0;
 
 // ------------------------------------------------------------------------------------------
 // fp32 weight stream.  One thread per destination float.
-//   group g of a pass -> [slot c = gate*2 + e][quad q][unit pair ug 0..63][4 k]
-//   hidden unit j = pass*128 + 2*ug + e ; k = kGk*(group index within part) + 4*q + kk
+//   group g of a pass -> [gate][k-pair p][unit pair ug 0..63][(e0,2p) (e1,2p) (e0,2p+1) (e1,2p+1)]
+//   hidden unit j = pass*128 + 2*ug + e ; k = kGk*(group index within part) + 2*p + {0,1}
 // ------------------------------------------------------------------------------------------
 __global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out0)
 {
@@ -22,10 +22,9 @@ __global__ void pack_weights_f32_kernel(fpc_weights w, float *__restrict__ out0)
     if (t < kStreamFloats) {
         int g = t / kGroupFloats;
         int r = t - g * kGroupFloats;
-        // [slot c][quad q][unit pair ug][4 k]
-        int c = r / (kGk * 64), r2 = r - c * (kGk * 64);
-        int q = r2 / 256, ug = (r2 >> 2) & 63, kk = 4 * q + (r2 & 3);
-        int gate = c >> 1, e = c & 1;
+        // [gate][k-pair p][unit pair ug][(e0,2p) (e1,2p) (e0,2p+1) (e1,2p+1)]
+        int gate = r / ((kGk / 2) * 256), r2 = r - gate * ((kGk / 2) * 256);
+        int pq = r2 / 256, ug = (r2 >> 2) & 63, kk = 2 * pq + ((r2 >> 1) & 1), e = r2 & 1;
         float v = 0.0f;
         if (g < 3 * kG1) {
             int pass = g / kG1, gi = g - pass * kG1;

@@ -159,6 +159,44 @@ __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint3
         "l"(gsrc), "r"(bytes), "r"(smem_u32(bar))
         : "memory");
 }
+// packed fp32 FMA on a register pair: d.x = fma(a.x, b, c.x), d.y = fma(a.y, b, c.y), each lane IEEE round-to-nearest
+// (PTX fma.rn.f32x2, SASS FFMA2 with the scalar-broadcast operand form).  Half the issue slots of two FFMAs and the
+// 64-bit operands straddle both register banks.
+__device__ __forceinline__ float2 fma2(float2 a, float b, float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+
+// d = a * b + c on both lanes with a full pair for b
+__device__ __forceinline__ float2 fma2(float2 a, float2 b, float2 c)
+{
+    unsigned long long ra, rb, rc, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b.x), "f"(b.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
+    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
+// d = a - b on both lanes (add.rn.f32x2 with the second operand negated; exact IEEE subtraction per lane)
+__device__ __forceinline__ float2 sub2(float2 a, float2 b)
+{
+    unsigned long long ra, rb, rd;
+    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
+    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(-b.x), "f"(-b.y));
+    asm("add.rn.f32x2 %0, %1, %2;" : "=l"(rd) : "l"(ra), "l"(rb));
+    float2 d;
+    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
+    return d;
+}
 __device__ __forceinline__ void named_bar_sync(int id, int nthreads)
 {
     asm volatile("bar.sync %0, %1;" ::"r"(id), "r"(nthreads) : "memory");

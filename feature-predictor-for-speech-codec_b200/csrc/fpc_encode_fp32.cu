@@ -71,21 +71,6 @@ struct Pipe {
 // buffer, barrier probed two groups ahead -- measured 20-25 % SLOWER on B200 than this plain loop:
 // 392 k vs 316 k cycles per frame for the GRU stage; ptxas schedules the simple form better.)
 // ------------------------------------------------------------------------------------------
-// packed fp32 FMA on a register pair: d.x = fma(a.x, b, c.x), d.y = fma(a.y, b, c.y), each lane IEEE round-to-nearest
-// (PTX fma.rn.f32x2, SASS FFMA2 with the scalar-broadcast operand form).  Half the issue slots of two FFMAs and the
-// 64-bit operands straddle both register banks.
-__device__ __forceinline__ float2 fma2(float2 a, float b, float2 c)
-{
-    unsigned long long ra, rb, rc, rd;
-    asm("mov.b64 %0, {%1, %2};" : "=l"(ra) : "f"(a.x), "f"(a.y));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rb) : "f"(b), "f"(b));
-    asm("mov.b64 %0, {%1, %2};" : "=l"(rc) : "f"(c.x), "f"(c.y));
-    asm("fma.rn.f32x2 %0, %1, %2, %3;" : "=l"(rd) : "l"(ra), "l"(rb), "l"(rc));
-    float2 d;
-    asm("mov.b64 {%0, %1}, %2;" : "=f"(d.x), "=f"(d.y) : "l"(rd));
-    return d;
-}
-
 template <int TU>
 __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], float2 (&an)[TU], int ng,
                                           const float *__restrict__ arow, int lda, const float4 *__restrict__ ring,

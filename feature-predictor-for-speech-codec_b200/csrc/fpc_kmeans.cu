@@ -43,22 +43,24 @@ __device__ __forceinline__ float screen_threshold(double best, float abs_slack)
 
 __device__ __forceinline__ float screen17(const float (&x)[kDim], const float *__restrict__ c)
 {
+    // packed lanes: (d, d+1) pairs through add.rn.f32x2 / fma.rn.f32x2 -- the same per-lane IEEE operations as the
+    // scalar form (t = x - c, acc = fma(t, t, acc)), half the instructions
     const float4 c0 = *reinterpret_cast<const float4 *>(c);
     const float4 c1 = *reinterpret_cast<const float4 *>(c + 4);
     const float4 c2 = *reinterpret_cast<const float4 *>(c + 8);
     const float4 c3 = *reinterpret_cast<const float4 *>(c + 12);
     const float c16 = c[16];
-    float a = 0.0f, b = 0.0f, t;
-    t = x[0] - c0.x; a = __fmaf_rn(t, t, a);   t = x[1] - c0.y; b = __fmaf_rn(t, t, b);
-    t = x[2] - c0.z; a = __fmaf_rn(t, t, a);   t = x[3] - c0.w; b = __fmaf_rn(t, t, b);
-    t = x[4] - c1.x; a = __fmaf_rn(t, t, a);   t = x[5] - c1.y; b = __fmaf_rn(t, t, b);
-    t = x[6] - c1.z; a = __fmaf_rn(t, t, a);   t = x[7] - c1.w; b = __fmaf_rn(t, t, b);
-    t = x[8] - c2.x; a = __fmaf_rn(t, t, a);   t = x[9] - c2.y; b = __fmaf_rn(t, t, b);
-    t = x[10] - c2.z; a = __fmaf_rn(t, t, a);  t = x[11] - c2.w; b = __fmaf_rn(t, t, b);
-    t = x[12] - c3.x; a = __fmaf_rn(t, t, a);  t = x[13] - c3.y; b = __fmaf_rn(t, t, b);
-    t = x[14] - c3.z; a = __fmaf_rn(t, t, a);  t = x[15] - c3.w; b = __fmaf_rn(t, t, b);
-    t = x[16] - c16; a = __fmaf_rn(t, t, a);
-    return a + b;
+    float2 acc = make_float2(0.0f, 0.0f), t;
+    t = sub2(make_float2(x[0], x[1]), make_float2(c0.x, c0.y)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[2], x[3]), make_float2(c0.z, c0.w)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[4], x[5]), make_float2(c1.x, c1.y)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[6], x[7]), make_float2(c1.z, c1.w)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[8], x[9]), make_float2(c2.x, c2.y)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[10], x[11]), make_float2(c2.z, c2.w)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[12], x[13]), make_float2(c3.x, c3.y)); acc = fma2(t, t, acc);
+    t = sub2(make_float2(x[14], x[15]), make_float2(c3.z, c3.w)); acc = fma2(t, t, acc);
+    const float tl = x[16] - c16;
+    return __fmaf_rn(tl, tl, acc.x) + acc.y;
 }
 
 __device__ __forceinline__ double exact17(const float (&x)[kDim], const double *__restrict__ c)

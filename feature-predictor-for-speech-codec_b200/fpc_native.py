@@ -23,7 +23,7 @@ EXPORTS = (
     "fpc_encode_workspace_bytes", "fpc_encode", "fpc_decode", "fpc_index_histogram",
     "fpc_vq_quantize_packed", "fpc_scl_quantize",
     "fpc_kmeans_workspace_bytes", "fpc_kmeans_assign_accumulate", "fpc_kmeans_finalize", "fpc_kmeans_gather",
-    "fpc_selftest_umma", "fpc_debug_set_phase_buffer",
+    "fpc_selftest_umma", "fpc_debug_set_phase_buffer", "fpc_ceps2lpc",
 )
 
 
@@ -101,6 +101,7 @@ def lib():
     L.fpc_kmeans_gather.argtypes = [vp, ci, vp, cl, vp, vp]
     L.fpc_selftest_umma.argtypes = [vp, vp, ci, ci, vp, vp]
     L.fpc_debug_set_phase_buffer.argtypes = [vp]
+    L.fpc_ceps2lpc.argtypes = [vp, cl, ci, vp, vp, vp, vp]
     _lib = L
     return L
 

@@ -18,6 +18,7 @@
  *   fpc_kmeans_assign_accumulate <- quantization/cb_func.py:56-68,82-86  find_nearest + sums
  *   fpc_kmeans_finalize        <- quantization/cb_func.py:88-97    divide, cluster statistics
  *   fpc_kmeans_gather          <- quantization/cb_func.py:103-112  quantize
+ *   fpc_ceps2lpc               <- ceps2lpc/ceps2lpc_vct.py:122-162 ceps2lpc_v
  *
  * Conventions
  *   - Plain C: pointers, sizes, a stream handle.  No torch / C++ types cross this boundary.
@@ -201,6 +202,14 @@ int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, d
  * self-test of the tensor-core plumbing (tcgen05.mma / TMEM) the bf16 predictor is built on:
  * d_out (128,N) f32 = A (128,K) bf16 x B (N,K) bf16 ^T.  16 <= N <= 256, N % 16 == 0, K % 16 == 0.
  * ------------------------------------------------------------------------------------------- */
+/* ---------------------------------------------------------------------------------------------
+ * cepstrum -> LPC  (ceps2lpc/ceps2lpc_vct.py:122-162 ceps2lpc_v, the step after Wavernn.encoder in
+ * synthesis_qtz.py:158-160 and generate_qtz_features.py:61-64)
+ * d_ceps (n, stride) float32, the first 18 columns of a row are the de-normalised cepstrum; d_lpc (n,16);
+ * d_err (n) final prediction error or NULL; d_rc (n,16) reflection coefficients or NULL.
+ * ------------------------------------------------------------------------------------------- */
+int fpc_ceps2lpc(const float *d_ceps, long n, int stride, float *d_lpc, float *d_err, float *d_rc, void *stream);
+
 /* debug aid: d_buf = 8 int64 counters in device memory (zeroed by the caller) or NULL to switch off;
  * CTA 0 of fpc_encode (fp32) adds the SM cycles it spent in [GRU, FC, thresholds+scalar, VQ, feedback] and the
  * number of frames.  Used by tools/phase_profile.py; not part of the reference-facing surface. */

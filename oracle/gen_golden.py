@@ -199,8 +199,27 @@ def run_kmeans_case():
     print("kmeans           done", flush=True)
 
 
+def run_ceps2lpc_case():
+    """ceps2lpc_v (ceps2lpc/ceps2lpc_vct.py:122-162) on de-normalised synthetic cepstra (x 24.1, as the callers do at
+    synthesis_qtz.py:158) incl. an all-zero frame and a ramp."""
+    import importlib.util
+    import torch
+    ref_shim.load_reference()
+    spec = importlib.util.spec_from_file_location("ref_ceps2lpc", os.path.join(ref_shim.REFERENCE_SRC, "ceps2lpc", "ceps2lpc_vct.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    x = (S.make_features(4, 100, first_utt=300) * 24.1).reshape(-1, 20).astype(np.float32)
+    x[5] = 0
+    x[17, :18] = np.linspace(-3, 3, 18)
+    e, lpc, rc = mod.ceps2lpc_v(torch.tensor(x))
+    np.savez_compressed(os.path.join(GOLDEN, "ceps2lpc.npz"), x=x, lpc=lpc.numpy(), e_last=np.float32(float(e)),
+                        rc_last=rc.numpy())
+    print("ceps2lpc         done", flush=True)
+
+
 CASES = {
     "forward": run_forward_case,
+    "ceps2lpc": run_ceps2lpc_case,
     "quantizers": run_quantizer_case,
     "kmeans": run_kmeans_case,
     # BASELINE.json configs[0]: 3 utterances x 3 s, README thresholds

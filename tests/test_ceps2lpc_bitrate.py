@@ -1,0 +1,81 @@
+"""Rows f2 / f4 of the scope table: cepstrum -> LPC and the codebook-usage bitrate report.
+
+ceps2lpc tolerance.  The Levinson recursion runs on an autocorrelation with a -40 dB noise floor, i.e. its
+condition number is ~1e3-1e4: the 3e-6 relative differences between torch's float32 `10**x` / FFT and any other
+correctly rounded evaluation already move LPC coefficients by up to 5e-3 (measured between the reference and the
+NumPy restatement).  The recursion also has two early exits (ceps2lpc_vct.py:82-85) -- discontinuities: a frame
+whose error sits on a threshold may run one iteration more or less (2 of 10 000 frames between GPU and oracle).
+Stated tolerance, on frames that leave the recursion at the same iteration: LPC within 1e-2 abs, reflection
+coefficients within 3e-3, final prediction error within 5e-3 relative; the exit iteration may differ on at most
+0.1 % of the frames."""
+import os
+import sys
+
+import numpy as np
+import pytest
+
+from conftest import ROOT
+from helpers import load_golden
+
+LPC_TOL, RC_TOL, ERR_RTOL, EXIT_FRACTION = 1e-2, 3e-3, 5e-3, 1e-3
+
+
+def test_ceps2lpc_oracle_matches_reference_golden():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ceps2lpc_oracle as C
+    g = load_golden("ceps2lpc")
+    lpc, err, rc = C.ceps2lpc(g["x"])
+    assert np.abs(lpc - g["lpc"]).max() <= LPC_TOL
+    assert np.abs(rc[-1] - g["rc_last"]).max() <= RC_TOL
+    assert abs(err[-1] - float(g["e_last"])) <= ERR_RTOL * float(g["e_last"])
+    assert np.all(lpc[5] == lpc[5]) and np.isfinite(lpc).all()       # the all-zero frame is well defined
+
+
+def test_bitrate_report_matches_reference_entropy():
+    import fpc_bitrate as B
+    g = np.random.Generator(np.random.Philox(key=5))
+    h = g.integers(0, 50, 256).astype(np.float64)
+    ref = h / h.sum()
+    want = np.sum(-ref * np.log2(ref + 1e-20))
+    assert B.cal_entropy(h.copy()) == want                   # generate_qtz_features.py:94-101, bit for bit
+    cb_tot = [h, 0, np.ones(1024), np.ones(1024), 0]          # every frame above threshold, uniform VQ usage
+    cb_tot[0] = h * (1024.0 / h.sum())
+    rep = B.bitrate_report(cb_tot)
+    assert rep["frames"] == pytest.approx(1024.0)
+    assert rep["entropy_bits"][2] == pytest.approx(10.0) and rep["fixed_bits"][0] == 8.0
+    assert rep["bits_per_frame_fixed_length"] == pytest.approx(2 + 8 + 10 + 10)
+    assert rep["kbps_fixed_length"] == pytest.approx(3.0)
+
+
+@pytest.mark.gpu
+def test_ceps2lpc_gpu_vs_oracle_and_reference(synth):
+    import torch
+    if not torch.cuda.is_available():
+        pytest.fail("needs a CUDA device")
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import ceps2lpc_oracle as C
+    from ceps2lpc.ceps2lpc_vct import ceps2lpc_v, ceps2lpc_device
+    g = load_golden("ceps2lpc")
+    e, lpc, rc = ceps2lpc_v(torch.from_numpy(g["x"]))             # CPU tensor in, like synthesis_qtz.py:159
+    assert lpc.shape == (len(g["x"]), 16) and lpc.dtype == torch.float32 and not lpc.is_cuda
+    assert np.abs(lpc.numpy() - g["lpc"]).max() <= LPC_TOL         # vs the reference itself
+    assert np.abs(rc.numpy() - g["rc_last"]).max() <= RC_TOL
+    assert abs(float(e) - float(g["e_last"])) <= ERR_RTOL * float(g["e_last"])
+    # larger seeded batch against the oracle, all frames
+    x = (synth.make_features(40, 250, first_utt=9000) * 24.1).reshape(-1, 20).astype(np.float32)
+    lo, eo, rco = C.ceps2lpc(x)
+    ld, ed, rd = ceps2lpc_device(torch.from_numpy(x).cuda())
+    torch.cuda.synchronize()
+    rdn = rd.cpu().numpy().astype(np.float64)
+    same = (rdn != 0).sum(1) == (rco != 0).sum(1)                  # left the recursion at the same iteration
+    assert (~same).mean() <= EXIT_FRACTION
+    assert np.abs(ld.cpu().numpy() - lo)[same].max() <= LPC_TOL
+    assert np.abs(rdn - rco)[same].max() <= RC_TOL
+    assert np.all((np.abs(ed.cpu().numpy() - eo) <= ERR_RTOL * np.abs(eo))[same])
+    # size-independent property at full scale: the LPC filter applied to its own autocorrelation leaves an
+    # error <= ac[0] and every reflection coefficient is inside the unit circle (stable synthesis filter)
+    big = torch.from_numpy(np.tile(x, (410, 1))[:4096 * 1000]).cuda()
+    lb, eb, rb = ceps2lpc_device(big)
+    torch.cuda.synchronize()
+    assert torch.isfinite(lb).all() and (rb.abs() < 1.0).all() and (eb > 0).all()
+    assert torch.equal(lb[:len(x)], ld)                            # independent of batch position

@@ -182,7 +182,6 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
         mbar_fence_init();
     }
     __syncthreads();
-
     // ---------------- producer warpgroup (only one lane works; it hands its registers over) ----------------
     if (warp >= kComputeThreads / 32) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");

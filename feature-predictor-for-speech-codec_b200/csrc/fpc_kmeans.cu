@@ -6,16 +6,17 @@
 //   update       (:71-100)  per-centroid float64 sums and counts, codebook = sum / (count + 1e-20)
 //   quantize     (:103-112) nearest-centroid gather
 //
-// Exactness.  The assignment is decided by EXACT float64 direct-form distances evaluated with
-// numpy's roundings (dist17<double>, fpc_vq.cuh), so indices are bit-identical to the
-// reference's, ties included.  To avoid paying 51 FP64 operations for every (vector, centroid)
-// pair, each pair is first screened in fp32: s = sum_d fma(t, t, .) with t = x_d - (float)c_d.
-// With delta_d = |t32_d - t64_d| <= 2^-24 (|c_d| + |t_d|) and 2ab <= g a^2 + b^2/g (g = 2^-12):
-//     |s - d64| <= (2^-12 + 2^-19) d64 + 2^-34 max_k ||c_k||^2          
-// so with REL = 2^-10 and ABS = 2^-32 Cmax^2 + 1e-30 (both carry a >= 2x safety factor, which
-// also absorbs rounding `best` to fp32), s > best (1 + REL) + ABS proves d64 > best: that
-// centroid cannot win (a later index also loses ties) and is skipped.  Every survivor is
-// re-evaluated in float64.  The screen only removes provable losers; it never picks a winner.
+// Exactness.  The reference decides by float64 direct-form distances (numpy's roundings, dist17<double> in
+// fpc_vq.cuh reproduces them), first minimum on ties; the indices here are bit-identical to that.  To avoid 51 FP64
+// operations per (vector, centroid) pair every pair is screened in fp32 with the expanded form
+//     s_k = ||c_k||^2 - 2 <x, c_k>             (8 packed FMAs + 1 FMA per pair; d_k = s_k + ||x||^2)
+// on the fp32 shadow (float)c_k.  With u = 2^-24 and R = (||x|| + ||c_k||)^2 the 18 FMA roundings, the rounding of
+// the shadow and of the stored norm give |s_k - (d_k - ||x||^2)| <= 21 u R (numpy's own float64 evaluation of d_k
+// is exact at this scale), so two screened values of one vector compare with error <= 42 u R.  One divergence-free
+// sweep keeps the two smallest s_k; with the per-vector slack A = 128 u (||x|| + Cmax)^2 (rounded up), a runner-up
+// more than A above the smallest proves the smallest is the exact argmin -- no float64 work at all.  Otherwise
+// (near-ties, duplicate centroids) the candidates within A of the smallest are re-evaluated in float64, ascending
+// k with strict <.  The screen never picks a winner it cannot prove.
 //
 // Sums.  The reference accumulates in data order on one thread.  Here every CTA first reduces
 // its vectors into per-warp-aggregated float64 atomics on the global (K,17) table; the order
@@ -31,36 +32,24 @@ constexpr int kKmThreads = 512;
 constexpr int kKmLd64 = 18;   // float64 codeword row stride in shared memory (16-byte aligned rows)
 constexpr int kKmLd32 = 20;   // float32 shadow row stride (float4 aligned)
 
-#define FPC_KM_SCREEN_REL 9.765625e-04f            /* 2^-10 */
-#define FPC_KM_SCREEN_ABS_SCALE 2.3283064365386963e-10f /* 2^-32 */
-
-__device__ __forceinline__ float screen_threshold(double best, float abs_slack)
+// s = cn + sum_d xm_d * c_d  (xm = -2 x), packed over (d, d+1) pairs; row = 16 floats, then c16, then ||c||^2
+__device__ __forceinline__ float screen17(const float2 (&xm)[8], float xm16, const float *__restrict__ c)
 {
-    // round best UP to fp32 so the threshold never undershoots
-    const float bf = __double2float_ru(best);
-    return __fadd_ru(__fmaf_ru(bf, FPC_KM_SCREEN_REL, bf), abs_slack);
-}
-
-__device__ __forceinline__ float screen17(const float (&x)[kDim], const float *__restrict__ c)
-{
-    // packed lanes: (d, d+1) pairs through add.rn.f32x2 / fma.rn.f32x2 -- the same per-lane IEEE operations as the
-    // scalar form (t = x - c, acc = fma(t, t, acc)), half the instructions
     const float4 c0 = *reinterpret_cast<const float4 *>(c);
     const float4 c1 = *reinterpret_cast<const float4 *>(c + 4);
     const float4 c2 = *reinterpret_cast<const float4 *>(c + 8);
     const float4 c3 = *reinterpret_cast<const float4 *>(c + 12);
-    const float c16 = c[16];
-    float2 acc = make_float2(0.0f, 0.0f), t;
-    t = sub2(make_float2(x[0], x[1]), make_float2(c0.x, c0.y)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[2], x[3]), make_float2(c0.z, c0.w)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[4], x[5]), make_float2(c1.x, c1.y)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[6], x[7]), make_float2(c1.z, c1.w)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[8], x[9]), make_float2(c2.x, c2.y)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[10], x[11]), make_float2(c2.z, c2.w)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[12], x[13]), make_float2(c3.x, c3.y)); acc = fma2(t, t, acc);
-    t = sub2(make_float2(x[14], x[15]), make_float2(c3.z, c3.w)); acc = fma2(t, t, acc);
-    const float tl = x[16] - c16;
-    return __fmaf_rn(tl, tl, acc.x) + acc.y;
+    const float2 tail = *reinterpret_cast<const float2 *>(c + 16);      // (c16, ||c||^2)
+    float2 acc = make_float2(tail.y, 0.0f);
+    acc = fma2(make_float2(c0.x, c0.y), xm[0], acc);
+    acc = fma2(make_float2(c0.z, c0.w), xm[1], acc);
+    acc = fma2(make_float2(c1.x, c1.y), xm[2], acc);
+    acc = fma2(make_float2(c1.z, c1.w), xm[3], acc);
+    acc = fma2(make_float2(c2.x, c2.y), xm[4], acc);
+    acc = fma2(make_float2(c2.z, c2.w), xm[5], acc);
+    acc = fma2(make_float2(c3.x, c3.y), xm[6], acc);
+    acc = fma2(make_float2(c3.z, c3.w), xm[7], acc);
+    return __fmaf_rn(tail.x, xm16, acc.x) + acc.y;
 }
 
 __device__ __forceinline__ double exact17(const float (&x)[kDim], const double *__restrict__ c)
@@ -86,6 +75,12 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
         cb32[k * kKmLd32 + d] = (float)v;
     }
     __syncthreads();
+    for (int k = threadIdx.x; k < K; k += kKmThreads) {          // ||c_k||^2 in float64, rounded, next to c16
+        double n2 = 0.0;
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) n2 += cb64[k * kKmLd64 + d] * cb64[k * kKmLd64 + d];
+        cb32[k * kKmLd32 + 17] = (float)n2;
+    }
     // Cmax^2 = max_k ||c_k||^2 (fp32, rounded up) for the absolute slack of the screen
     __shared__ float s_c2[kKmThreads / 32];
     {
@@ -103,9 +98,9 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
         if ((threadIdx.x & 31) == 0) s_c2[threadIdx.x >> 5] = c2;
     }
     __syncthreads();
-    float abs_slack = 0.0f;
-    for (int w = 0; w < kKmThreads / 32; ++w) abs_slack = fmaxf(abs_slack, s_c2[w]);
-    abs_slack = __fadd_ru(__fmul_ru(abs_slack, FPC_KM_SCREEN_ABS_SCALE), 1e-30f);
+    float cmax2 = 0.0f;
+    for (int w = 0; w < kKmThreads / 32; ++w) cmax2 = fmaxf(cmax2, s_c2[w]);
+    const float cmax = __fsqrt_ru(cmax2);                      // upper bound of max ||c_k||
 
     const int lane = threadIdx.x & 31;
     const long stride = (long)gridDim.x * kKmThreads;
@@ -117,17 +112,39 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
 #pragma unroll
         for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + i * kDim + d) : 0.0f;
 
-        // exact distance to centroid 0 seeds the running minimum (np.argmin: first minimum)
-        double best = exact17(x, cb64);
+        // per-vector screen constants: xm = -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, all rounded up
+        float2 xm[8];
+#pragma unroll
+        for (int d = 0; d < 8; ++d) xm[d] = make_float2(-2.0f * x[2 * d], -2.0f * x[2 * d + 1]);
+        const float xm16 = -2.0f * x[16];
+        float nx = 0.0f;
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) nx = __fmaf_ru(x[d], x[d], nx);
+        const float rr = __fadd_ru(__fsqrt_ru(nx), cmax);
+        const float slack = __fadd_ru(__fmul_ru(__fmul_ru(rr, rr), 7.62939453125e-6f), 1e-30f);   // 128 * 2^-24
+        // One divergence-free sweep keeps the two smallest screened values.  All s_k share the ||x||^2 term, so
+        // two of them compare with error <= 2 * 21 u R: if the runner-up is more than the slack above the smallest,
+        // the smallest is the exact argmin (no float64 work at all); otherwise the vector is ambiguous (near-tie,
+        // duplicate centroids) and the candidates inside the slack are decided in float64 exactly as numpy does,
+        // ascending k with strict <, i.e. first minimum.
+        float m1 = __int_as_float(0x7f800000), m2 = m1;
         int bi = 0;
-        float thr = screen_threshold(best, abs_slack);
-        for (int k = 1; k < K; ++k) {
-            const float s = screen17(x, cb32 + k * kKmLd32);
-            if (s <= thr) {   // cannot be excluded: decide in float64 exactly as numpy does
-                const double d = exact17(x, cb64 + k * kKmLd64);
-                if (d < best) {
-                    best = d; bi = k;
-                    thr = screen_threshold(best, abs_slack);
+        for (int k = 0; k < K; ++k) {
+            const float s = screen17(xm, xm16, cb32 + k * kKmLd32);
+            const bool p = s < m1;
+            m2 = fminf(m2, fmaxf(m1, s));
+            m1 = fminf(m1, s);
+            bi = p ? k : bi;
+        }
+        const float thr = __fadd_ru(m1, slack);
+        if (!(m2 > thr)) {
+            double best = 0.0;
+            bool have = false;
+            for (int k = 0; k < K; ++k) {
+                const float s = screen17(xm, xm16, cb32 + k * kKmLd32);
+                if (s <= thr) {
+                    const double d = exact17(x, cb64 + k * kKmLd64);
+                    if (!have || d < best) { best = d; bi = k; have = true; }
                 }
             }
         }

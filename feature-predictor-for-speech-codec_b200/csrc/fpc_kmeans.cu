@@ -28,18 +28,28 @@
 
 namespace fpc {
 
-constexpr int kKmThreads = 512;
+constexpr int kKmThreads = 256;
+constexpr int kKmV = 4;        // vectors per thread: the 5 broadcast LDS of a centroid row serve 4 screens (and 4-way ILP)
 constexpr int kKmLd64 = 18;   // float64 codeword row stride in shared memory (16-byte aligned rows)
 constexpr int kKmLd32 = 20;   // float32 shadow row stride (float4 aligned)
 
-// s = cn + sum_d xm_d * c_d  (xm = -2 x), packed over (d, d+1) pairs; row = 16 floats, then c16, then ||c||^2
-__device__ __forceinline__ float screen17(const float2 (&xm)[8], float xm16, const float *__restrict__ c)
+// centroid row in registers: 16 floats, then (c16, ||c||^2)
+struct KmRow { float4 c0, c1, c2, c3; float2 tail; };
+__device__ __forceinline__ KmRow load_row(const float *__restrict__ c)
 {
-    const float4 c0 = *reinterpret_cast<const float4 *>(c);
-    const float4 c1 = *reinterpret_cast<const float4 *>(c + 4);
-    const float4 c2 = *reinterpret_cast<const float4 *>(c + 8);
-    const float4 c3 = *reinterpret_cast<const float4 *>(c + 12);
-    const float2 tail = *reinterpret_cast<const float2 *>(c + 16);      // (c16, ||c||^2)
+    KmRow r;
+    r.c0 = *reinterpret_cast<const float4 *>(c);
+    r.c1 = *reinterpret_cast<const float4 *>(c + 4);
+    r.c2 = *reinterpret_cast<const float4 *>(c + 8);
+    r.c3 = *reinterpret_cast<const float4 *>(c + 12);
+    r.tail = *reinterpret_cast<const float2 *>(c + 16);
+    return r;
+}
+// s = cn + sum_d xm_d * c_d  (xm = -2 x), packed over (d, d+1) pairs
+__device__ __forceinline__ float screen17(const float2 (&xm)[8], float xm16, const KmRow &row)
+{
+    const float4 c0 = row.c0, c1 = row.c1, c2 = row.c2, c3 = row.c3;
+    const float2 tail = row.tail;
     float2 acc = make_float2(tail.y, 0.0f);
     acc = fma2(make_float2(c0.x, c0.y), xm[0], acc);
     acc = fma2(make_float2(c0.z, c0.w), xm[1], acc);
@@ -103,81 +113,101 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
     const float cmax = __fsqrt_ru(cmax2);                      // upper bound of max ||c_k||
 
     const int lane = threadIdx.x & 31;
-    const long stride = (long)gridDim.x * kKmThreads;
+    const long per_round = (long)kKmThreads * kKmV;
+    const long stride = (long)gridDim.x * per_round;
     const long nround = (N + stride - 1) / stride;
     for (long it = 0; it < nround; ++it) {
-        const long i = it * stride + (long)blockIdx.x * kKmThreads + threadIdx.x;
-        const bool valid = i < N;
-        float x[kDim];
+        const long i0 = it * stride + (long)blockIdx.x * per_round + threadIdx.x;     // vectors i0 + j * kKmThreads
+        float2 xm[kKmV][8];
+        float xm16[kKmV], slack[kKmV], m1[kKmV], m2[kKmV];
+        int bi[kKmV];
 #pragma unroll
-        for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + i * kDim + d) : 0.0f;
-
-        // per-vector screen constants: xm = -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, all rounded up
-        float2 xm[8];
+        for (int j = 0; j < kKmV; ++j) {
+            const long i = i0 + (long)j * kKmThreads;
+            float x[kDim];
 #pragma unroll
-        for (int d = 0; d < 8; ++d) xm[d] = make_float2(-2.0f * x[2 * d], -2.0f * x[2 * d + 1]);
-        const float xm16 = -2.0f * x[16];
-        float nx = 0.0f;
+            for (int d = 0; d < kDim; ++d) x[d] = i < N ? __ldg(data + i * kDim + d) : 0.0f;
+            // per-vector screen constants: xm = -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, rounded up
 #pragma unroll
-        for (int d = 0; d < kDim; ++d) nx = __fmaf_ru(x[d], x[d], nx);
-        const float rr = __fadd_ru(__fsqrt_ru(nx), cmax);
-        const float slack = __fadd_ru(__fmul_ru(__fmul_ru(rr, rr), 7.62939453125e-6f), 1e-30f);   // 128 * 2^-24
-        // One divergence-free sweep keeps the two smallest screened values.  All s_k share the ||x||^2 term, so
-        // two of them compare with error <= 2 * 21 u R: if the runner-up is more than the slack above the smallest,
-        // the smallest is the exact argmin (no float64 work at all); otherwise the vector is ambiguous (near-tie,
-        // duplicate centroids) and the candidates inside the slack are decided in float64 exactly as numpy does,
-        // ascending k with strict <, i.e. first minimum.
-        float m1 = __int_as_float(0x7f800000), m2 = m1;
-        int bi = 0;
-        for (int k = 0; k < K; ++k) {
-            const float s = screen17(xm, xm16, cb32 + k * kKmLd32);
-            const bool p = s < m1;
-            m2 = fminf(m2, fmaxf(m1, s));
-            m1 = fminf(m1, s);
-            bi = p ? k : bi;
+            for (int d = 0; d < 8; ++d) xm[j][d] = make_float2(-2.0f * x[2 * d], -2.0f * x[2 * d + 1]);
+            xm16[j] = -2.0f * x[16];
+            float nx = 0.0f;
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) nx = __fmaf_ru(x[d], x[d], nx);
+            const float rr = __fadd_ru(__fsqrt_ru(nx), cmax);
+            slack[j] = __fadd_ru(__fmul_ru(__fmul_ru(rr, rr), 7.62939453125e-6f), 1e-30f);   // 128 * 2^-24
+            m1[j] = __int_as_float(0x7f800000); m2[j] = m1[j]; bi[j] = 0;
         }
-        const float thr = __fadd_ru(m1, slack);
-        if (!(m2 > thr)) {
-            double best = 0.0;
-            bool have = false;
-            for (int k = 0; k < K; ++k) {
-                const float s = screen17(xm, xm16, cb32 + k * kKmLd32);
-                if (s <= thr) {
-                    const double d = exact17(x, cb64 + k * kKmLd64);
-                    if (!have || d < best) { best = d; bi = k; have = true; }
-                }
+        // One divergence-free sweep keeps the two smallest screened values of every vector.  All s_k of a vector
+        // share the ||x||^2 term, so two of them compare with error <= 2 * 21 u R: if the runner-up is more than
+        // the slack above the smallest, the smallest is the exact argmin (no float64 work at all); otherwise the
+        // vector is ambiguous (near-tie, duplicate centroids) and the candidates inside the slack are decided in
+        // float64 exactly as numpy does, ascending k with strict <, i.e. first minimum.
+        for (int k = 0; k < K; ++k) {
+            const KmRow row = load_row(cb32 + k * kKmLd32);
+#pragma unroll
+            for (int j = 0; j < kKmV; ++j) {
+                const float s = screen17(xm[j], xm16[j], row);
+                const bool p = s < m1[j];
+                m2[j] = fminf(m2[j], fmaxf(m1[j], s));
+                m1[j] = fminf(m1[j], s);
+                bi[j] = p ? k : bi[j];
             }
         }
-        if (valid && idx_out) idx_out[i] = bi;
-
-        // accumulate.  Small codebooks (the first steps of the grow-by-one schedule,
-        // cb_func.py:34-47) would hammer a handful of addresses, so there the lanes that chose
-        // the same centroid are merged first (uniform full-mask shuffles, ascending lane order).
-        if (sums) {
-            const int key = valid ? bi : -1;
-            if (K <= 32) {
-                const unsigned peers = __match_any_sync(0xffffffffu, key);
-                const int leader = __ffs(peers) - 1;
-                double acc[kDim];
 #pragma unroll
-                for (int d = 0; d < kDim; ++d) acc[d] = 0.0;
-                for (int src = 0; src < 32; ++src) {
-                    const bool take = (peers >> src) & 1u;
+        for (int j = 0; j < kKmV; ++j) {
+            const long i = i0 + (long)j * kKmThreads;
+            const bool valid = i < N;
+            const float thr = __fadd_ru(m1[j], slack[j]);
+            float x[kDim];
+            const bool need_x = (sums != nullptr) || !(m2[j] > thr);
+            if (need_x) {
 #pragma unroll
-                    for (int d = 0; d < kDim; ++d) {
-                        const double v = __shfl_sync(0xffffffffu, (double)x[d], src);
-                        if (take) acc[d] += v;
+                for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + i * kDim + d) : 0.0f;   // L1/L2 hit
+            }
+            if (!(m2[j] > thr)) {
+                double best = 0.0;
+                bool have = false;
+                for (int k = 0; k < K; ++k) {
+                    const float s = screen17(xm[j], xm16[j], load_row(cb32 + k * kKmLd32));
+                    if (s <= thr) {
+                        const double d = exact17(x, cb64 + k * kKmLd64);
+                        if (!have || d < best) { best = d; bi[j] = k; have = true; }
                     }
                 }
-                if (valid && lane == leader) {
+            }
+            const int b = bi[j];
+            if (valid && idx_out) idx_out[i] = b;
+
+            // accumulate.  Small codebooks (the first steps of the grow-by-one schedule, cb_func.py:34-47) would
+            // hammer a handful of addresses, so there the lanes that chose the same centroid are merged first
+            // (uniform full-mask shuffles, ascending lane order).
+            if (sums) {
+                const int key = valid ? b : -1;
+                if (K <= 32) {
+                    const unsigned peers = __match_any_sync(0xffffffffu, key);
+                    const int leader = __ffs(peers) - 1;
+                    double acc[kDim];
 #pragma unroll
-                    for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)bi * kDim + d, acc[d]);
-                    atomicAdd(counts + bi, (double)__popc(peers));
+                    for (int d = 0; d < kDim; ++d) acc[d] = 0.0;
+                    for (int src = 0; src < 32; ++src) {
+                        const bool take = (peers >> src) & 1u;
+#pragma unroll
+                        for (int d = 0; d < kDim; ++d) {
+                            const double v = __shfl_sync(0xffffffffu, (double)x[d], src);
+                            if (take) acc[d] += v;
+                        }
+                    }
+                    if (valid && lane == leader) {
+#pragma unroll
+                        for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)b * kDim + d, acc[d]);
+                        atomicAdd(counts + b, (double)__popc(peers));
+                    }
+                } else if (valid) {
+#pragma unroll
+                    for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)b * kDim + d, (double)x[d]);
+                    atomicAdd(counts + b, 1.0);
                 }
-            } else if (valid) {
-#pragma unroll
-                for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)bi * kDim + d, (double)x[d]);
-                atomicAdd(counts + bi, 1.0);
             }
         }
     }
@@ -271,7 +301,7 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
                                           (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4))));
         configured = (size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4);
     }
-    long blocks = (N + kKmThreads - 1) / kKmThreads;
+    long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;
     kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, d_sums, d_counts, d_idx);
     FPC_LAUNCH_CHECK();

@@ -1,4 +1,5 @@
 // fpc_api.cu -- C-ABI entry points of the encode / decode / quantiser paths (include/fpc_b200.h).
+#include <vector>
 #include "fpc_common.cuh"
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
@@ -120,9 +121,120 @@ int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, con
     P.mode = io->qtz ? kModeQuantize : kModeResidual;
     P.l1 = io->l1; P.l2 = io->l2;
     P.ntiles = 0;
+    P.f0 = 0; P.f1 = io->L; P.state = nullptr;
     P.prof = g_phase_buffer;
     if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
+}
+
+// ---- host-buffer form: time-chunked upload / compute / download pipeline ----
+namespace {
+struct HostPipe {
+    int device = -1;
+    cudaStream_t s_in = nullptr, s_out = nullptr;
+    std::vector<cudaEvent_t> ev;
+    int ensure(int dev, size_t nev)
+    {
+        if (device != dev) {           // one pipeline per process and device in use; rebuilt if the device changes
+            s_in = nullptr; s_out = nullptr; ev.clear(); device = dev;
+        }
+        if (!s_in) FPC_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        if (!s_out) FPC_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
+        while (ev.size() < nev) {
+            cudaEvent_t e;
+            FPC_CUDA_TRY(cudaEventCreateWithFlags(&e, cudaEventDisableTiming));
+            ev.push_back(e);
+        }
+        return FPC_OK;
+    }
+};
+HostPipe g_host_pipe;
+const int kHostWords[8] = {20, 20, 18, 18, 18, 1, 1, 4};   // feat, c_in, r, r_qtz, r_under, ind1, ind2, idx (4-byte words per frame)
+size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+}  // namespace
+
+size_t fpc_encode_host_workspace_bytes(int B, int L, int precision)
+{
+    if (B <= 0 || L <= 0) return 0;
+    size_t total = 0;
+    for (int i = 0; i < 8; ++i) total += align256((size_t)B * L * kHostWords[i] * 4);
+    if (precision == FPC_PREC_FP32) total += align256(encode_fp32_state_bytes(B));
+    return total;
+}
+
+int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_host_io *io,
+                    int precision, int chunks, void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    if (!d_packed_weights || !io) return FPC_ERR_ARG;
+    if (io->B < 0 || io->L < 0) return FPC_ERR_ARG;
+    if (io->B == 0 || io->L == 0) return FPC_OK;
+    if (!io->h_feat) return FPC_ERR_ARG;
+    if (io->qtz && !d_packed_codebooks) return FPC_ERR_ARG;
+    if (precision != FPC_PREC_FP32 && precision != FPC_PREC_BF16) return FPC_ERR_UNSUPPORTED;
+    const int B = io->B, L = io->L;
+    if (!d_workspace || workspace_bytes < fpc_encode_host_workspace_bytes(B, L, precision)) return FPC_ERR_WORKSPACE;
+    if (chunks <= 0) chunks = L / 48 < 1 ? 1 : (L / 48 > 16 ? 16 : L / 48);
+    if (chunks > L) chunks = L;
+    if (precision != FPC_PREC_FP32) chunks = 1;
+    if (chunks > 64) chunks = 64;
+
+    char *ws = (char *)d_workspace;
+    void *dev[8];
+    for (int i = 0; i < 8; ++i) { dev[i] = ws; ws += align256((size_t)B * L * kHostWords[i] * 4); }
+    float *state = precision == FPC_PREC_FP32 ? (float *)ws : nullptr;
+    void *host_out[8] = {nullptr, io->h_c_in, io->h_r, io->h_r_qtz, io->h_r_under, io->h_ind1, io->h_ind2, io->h_idx};
+
+    int devid = 0;
+    FPC_CUDA_TRY(cudaGetDevice(&devid));
+    HostPipe &hp = g_host_pipe;
+    { const int rc = hp.ensure(devid, (size_t)2 * chunks + 2); if (rc != FPC_OK) return rc; }
+    cudaStream_t st = (cudaStream_t)stream;
+    cudaEvent_t ev_start = hp.ev[2 * chunks], ev_done = hp.ev[2 * chunks + 1];
+    FPC_CUDA_TRY(cudaEventRecord(ev_start, st));            // everything queued before this call on `stream` goes first
+    FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, ev_start, 0));
+    FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, ev_start, 0));
+
+    EncodeParams P;
+    P.wstream = (const float *)d_packed_weights;
+    P.cb = (const char *)d_packed_codebooks;
+    P.feat = (const float *)dev[0];
+    P.mask = nullptr; P.rq_in = nullptr; P.pitch_in = nullptr;
+    P.c_in = (float *)dev[1]; P.r = (float *)dev[2]; P.r_qtz = (float *)dev[3]; P.r_under = (float *)dev[4];
+    P.ind1 = (float *)dev[5]; P.ind2 = (float *)dev[6]; P.idx = (int32_t *)dev[7];
+    P.B = B; P.L = L;
+    P.mode = io->qtz ? kModeQuantize : kModeResidual;
+    P.l1 = io->l1; P.l2 = io->l2;
+    P.ntiles = 0;
+    P.state = chunks > 1 ? state : nullptr;
+    P.prof = nullptr;
+
+    auto range = [&](int c) { return (int)((long long)L * c / chunks); };
+    // a frame range of a (B, L, words) array is a 2-D block: B rows of (f1 - f0) * words * 4 bytes, pitch L * words * 4
+    for (int c = 0; c < chunks; ++c) {
+        const int f0 = range(c), f1 = range(c + 1);
+        const size_t pitch = (size_t)L * kHostWords[0] * 4, off = (size_t)f0 * kHostWords[0] * 4;
+        FPC_CUDA_TRY(cudaMemcpy2DAsync((char *)dev[0] + off, pitch, (const char *)io->h_feat + off, pitch,
+                                       (size_t)(f1 - f0) * kHostWords[0] * 4, (size_t)B, cudaMemcpyHostToDevice, hp.s_in));
+        FPC_CUDA_TRY(cudaEventRecord(hp.ev[c], hp.s_in));
+    }
+    for (int c = 0; c < chunks; ++c) {
+        P.f0 = range(c); P.f1 = range(c + 1);
+        FPC_CUDA_TRY(cudaStreamWaitEvent(st, hp.ev[c], 0));
+        const int rc = precision == FPC_PREC_BF16 ? run_encode_bf16(P, st, 0) : run_encode_fp32(P, st, 0);
+        if (rc != FPC_OK) return rc;
+        FPC_CUDA_TRY(cudaEventRecord(hp.ev[chunks + c], st));
+        FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, hp.ev[chunks + c], 0));
+        for (int i = 1; i < 8; ++i) {
+            if (!host_out[i]) continue;
+            const size_t pitch = (size_t)L * kHostWords[i] * 4, off = (size_t)P.f0 * kHostWords[i] * 4;
+            FPC_CUDA_TRY(cudaMemcpy2DAsync((char *)host_out[i] + off, pitch, (const char *)dev[i] + off, pitch,
+                                           (size_t)(P.f1 - P.f0) * kHostWords[i] * 4, (size_t)B, cudaMemcpyDeviceToHost,
+                                           hp.s_out));
+        }
+    }
+    FPC_CUDA_TRY(cudaEventRecord(ev_done, hp.s_out));
+    FPC_CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));     // `stream` completes only after the last download
+    return FPC_OK;
 }
 
 int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *d_pitch, int B, int L, float *d_c_out,
@@ -141,6 +253,7 @@ int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *
     P.c_in = d_c_out; P.r = nullptr; P.r_qtz = nullptr; P.r_under = nullptr;
     P.ind1 = nullptr; P.ind2 = nullptr; P.idx = nullptr;
     P.B = B; P.L = L; P.mode = kModeDecode; P.l1 = 0.0f; P.l2 = 0.0f; P.ntiles = 0; P.prof = nullptr;
+    P.f0 = 0; P.f1 = L; P.state = nullptr;
     if (precision == FPC_PREC_BF16) return run_encode_bf16(P, (cudaStream_t)stream, 0);
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }

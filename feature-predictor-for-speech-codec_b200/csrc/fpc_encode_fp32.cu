@@ -186,7 +186,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     if (warp >= kComputeThreads / 32) {
         asm volatile("setmaxnreg.dec.sync.aligned.u32 40;");
         if (warp == kComputeThreads / 32 && lane == 0) {
-            const long long total = (long long)my_tiles * P.L * kGroupsPerFrame;
+            const long long total = (long long)my_tiles * (P.f1 - P.f0) * kGroupsPerFrame;
             const char *src = reinterpret_cast<const char *>(P.wstream) + (size_t)(blockIdx.x % kWeightReplicas) * kPackedF32ReplicaBytes;
             int s = 0, gf = 0;
             uint32_t wraps = 0;
@@ -222,12 +222,18 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int b0 = tile * MT;
         float *cur = setA, *nxt = setB;
-        for (int i = tid; i < S::kStateSet; i += kComputeThreads) cur[i] = 0.0f;   // h1 = h2 = None -> zeros
-        for (int i = tid; i < MT * kLdX; i += kComputeThreads) xin[i] = 0.0f;      // frame 0 input is all zero
+        float *carry = P.state ? P.state + (size_t)tile * (S::kStateSet + MT * kLdX) : nullptr;
+        if (carry && P.f0 > 0) {       // continue the recurrence where the launch of the previous frame range stopped
+            for (int i = tid; i < S::kStateSet; i += kComputeThreads) cur[i] = carry[i];
+            for (int i = tid; i < MT * kLdX; i += kComputeThreads) xin[i] = carry[S::kStateSet + i];
+        } else {
+            for (int i = tid; i < S::kStateSet; i += kComputeThreads) cur[i] = 0.0f;   // h1 = h2 = None -> zeros
+            for (int i = tid; i < MT * kLdX; i += kComputeThreads) xin[i] = 0.0f;      // frame 0 input is all zero
+        }
         for (int i = tid; i < MT * kLdR; i += kComputeThreads) rs[i] = 0.0f;
         named_bar_sync(1, kComputeThreads);
 
-        for (int fr = 0; fr < P.L; ++fr) {
+        for (int fr = P.f0; fr < P.f1; ++fr) {
             // element ownership for this frame: e = tid + 256 q -> (row u, feature j)
             float featv[NE], fov[NE], rsv[NE];
 #pragma unroll
@@ -411,6 +417,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
             if (prof) pt[kPhFrames] += 1;
             float *t = cur; cur = nxt; nxt = t;
         }
+        if (carry) {
+            for (int i = tid; i < S::kStateSet; i += kComputeThreads) carry[i] = cur[i];
+            for (int i = tid; i < MT * kLdX; i += kComputeThreads) carry[S::kStateSet + i] = xin[i];
+            named_bar_sync(1, kComputeThreads);
+        }
     }
     if (prof)
         for (int i = 0; i < kPhCount; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof) + (size_t)blockIdx.x * kPhCount + i, (unsigned long long)pt[i]);
@@ -460,8 +471,18 @@ static int pick_tu(int B, int sms)
     return best;
 }
 
+size_t encode_fp32_state_bytes(int B)
+{
+    const int sms = num_sms();
+    if (sms <= 0 || B <= 0) return 0;
+    const int mt = 4 * pick_tu(B, sms);
+    const size_t tiles = (size_t)(B + mt - 1) / mt;
+    return tiles * (size_t)(mt * (kLd1 + kLd2) + mt * kLdX) * sizeof(float);
+}
+
 int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu)
 {
+    if (P.f0 < 0 || P.f1 > P.L || P.f0 >= P.f1) return FPC_ERR_ARG;
     const int sms = num_sms();
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
     const int tu = force_tu > 0 ? force_tu : pick_tu(P.B, sms);

@@ -9,10 +9,17 @@
 // Exactness.  The reference decides by float64 direct-form distances (numpy's roundings, dist17<double> in
 // fpc_vq.cuh reproduces them), first minimum on ties; the indices here are bit-identical to that.  To avoid 51 FP64
 // operations per (vector, centroid) pair every pair is screened in fp32 with the expanded form
-//     s_k = ||c_k||^2 - 2 <x, c_k>             (8 packed FMAs + 1 FMA per pair; d_k = s_k + ||x||^2)
-// on the fp32 shadow (float)c_k.  With u = 2^-24 and R = (||x|| + ||c_k||)^2 the 18 FMA roundings, the rounding of
+//     s_k = ||c_k||^2 - 2 <x, c_k>             (one 17-step FMA chain seeded with ||c_k||^2; d_k = s_k + ||x||^2)
+// on the fp32 shadow (float)c_k.  With u = 2^-24 and R = (||x|| + ||c_k||)^2 the 17 FMA roundings, the rounding of
 // the shadow and of the stored norm give |s_k - (d_k - ||x||^2)| <= 21 u R (numpy's own float64 evaluation of d_k
-// is exact at this scale), so two screened values of one vector compare with error <= 42 u R.  One divergence-free
+// is exact at this scale), so two screened values of one vector compare with error <= 42 u R.
+// Issue form: a thread owns two vectors as the two lanes of fma.rn.f32x2 and sweeps eight centroids per step,
+//     acc[r] = (-2 x_d of vector 0, -2 x_d of vector 1) * broadcast(c[r][d]) + acc[r],   r = 0..7,
+// so 17 packed FMAs cover two (vector, centroid) pairs and the packed pair operand is the one the eight
+// consecutive instructions share.  That matters: on sm_100a FFMA2 issues every 2 cycles only when the 64-bit
+// pair operand comes from the operand-reuse cache; with three fresh 64-bit operands it takes 3
+// (tools/ubench_ffma2.cu).  The shadow is stored in blocks of four rows, transposed ([d][r], one LDS.128 per
+// dimension of four rows), with ||c||^2 as ready-made (n, n) pairs for the seed.  One divergence-free
 // sweep keeps the two smallest s_k; with the per-vector slack A = 128 u (||x|| + Cmax)^2 (rounded up), a runner-up
 // more than A above the smallest proves the smallest is the exact argmin -- no float64 work at all.  Otherwise
 // (near-ties, duplicate centroids) the candidates within A of the smallest are re-evaluated in float64, ascending
@@ -28,38 +35,26 @@
 
 namespace fpc {
 
-constexpr int kKmThreads = 256;
-constexpr int kKmV = 4;        // vectors per thread: the 5 broadcast LDS of a centroid row serve 4 screens (and 4-way ILP)
+constexpr int kKmThreads = 512;
+constexpr int kKmV = 2;        // vectors per thread: the 5 broadcast LDS of a centroid row serve 4 screens (and 4-way ILP)
 constexpr int kKmLd64 = 18;   // float64 codeword row stride in shared memory (16-byte aligned rows)
 constexpr int kKmLd32 = 20;   // float32 shadow row stride (float4 aligned)
+constexpr int kKmRows = 4;    // centroid rows per sweep step (the shadow is padded to a multiple)
+constexpr int kKmNB = 2;      // blocks per sweep step: 8 rows share each packed pair of vectors
+constexpr int kKmPad = kKmRows * kKmNB;     // rows the shadow is padded to
+constexpr int kStepRows = kKmRows * kKmNB;
+static_assert(kKmRows == 4, "the shadow block layout is one float4 per dimension");
 
-// centroid row in registers: 16 floats, then (c16, ||c||^2)
-struct KmRow { float4 c0, c1, c2, c3; float2 tail; };
-__device__ __forceinline__ KmRow load_row(const float *__restrict__ c)
+// Screen value of one (vector, centroid) pair: s = ||c||^2 + sum_d (-2 x_d) c_d as one ascending-d FMA chain seeded
+// with ||c||^2.  The sweep evaluates it two vectors at a time (one packed lane each, see below); this scalar form is
+// the same chain, so the rescan reproduces the sweep's value bit for bit.
+__device__ __forceinline__ float screen17(const float (&x)[kDim], const float *__restrict__ cb32, int k)
 {
-    KmRow r;
-    r.c0 = *reinterpret_cast<const float4 *>(c);
-    r.c1 = *reinterpret_cast<const float4 *>(c + 4);
-    r.c2 = *reinterpret_cast<const float4 *>(c + 8);
-    r.c3 = *reinterpret_cast<const float4 *>(c + 12);
-    r.tail = *reinterpret_cast<const float2 *>(c + 16);
-    return r;
-}
-// s = cn + sum_d xm_d * c_d  (xm = -2 x), packed over (d, d+1) pairs
-__device__ __forceinline__ float screen17(const float2 (&xm)[8], float xm16, const KmRow &row)
-{
-    const float4 c0 = row.c0, c1 = row.c1, c2 = row.c2, c3 = row.c3;
-    const float2 tail = row.tail;
-    float2 acc = make_float2(tail.y, 0.0f);
-    acc = fma2(make_float2(c0.x, c0.y), xm[0], acc);
-    acc = fma2(make_float2(c0.z, c0.w), xm[1], acc);
-    acc = fma2(make_float2(c1.x, c1.y), xm[2], acc);
-    acc = fma2(make_float2(c1.z, c1.w), xm[3], acc);
-    acc = fma2(make_float2(c2.x, c2.y), xm[4], acc);
-    acc = fma2(make_float2(c2.z, c2.w), xm[5], acc);
-    acc = fma2(make_float2(c3.x, c3.y), xm[6], acc);
-    acc = fma2(make_float2(c3.z, c3.w), xm[7], acc);
-    return __fmaf_rn(tail.x, xm16, acc.x) + acc.y;
+    const float *c = cb32 + (k >> 2) * (kKmLd32 * kKmRows) + (k & 3);
+    float s = c[18 * kKmRows + (k & 3)];      // ||c||^2 of row r = k & 3 sits at block slot 18*4 + 2r (c is offset by r)
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) s = __fmaf_rn(-2.0f * x[d], c[d * kKmRows], s);
+    return s;
 }
 
 __device__ __forceinline__ double exact17(const float (&x)[kDim], const double *__restrict__ c)
@@ -77,19 +72,26 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *cb64 = reinterpret_cast<double *>(smem);                              // [K][18]
-    float *cb32 = reinterpret_cast<float *>(smem + (size_t)K * kKmLd64 * 8);      // [K][20]
+    float *cb32 = reinterpret_cast<float *>(smem + (size_t)K * kKmLd64 * 8);      // [Kp][20]: c0..c16, -, ||c||^2 twice
+    const int Kp = (K + kKmPad - 1) / kKmPad * kKmPad;      // padded with rows that can never win (s = +inf)
+    // shadow layout: blocks of kKmRows = 4 rows, transposed: blk[d][r] for d < 17, blk[17] unused, then the four
+    // ||c||^2 as duplicated pairs (n0,n0,n1,n1 | n2,n2,n3,n3), so one LDS.128 feeds one dimension of four rows
+    for (int i = threadIdx.x; i < Kp * kKmLd32; i += kKmThreads)
+        cb32[i] = (i % (kKmLd32 * kKmRows)) >= 18 * kKmRows ? __int_as_float(0x7f800000) : 0.0f;
+    __syncthreads();
     for (int i = threadIdx.x; i < K * kDim; i += kKmThreads) {
         const int k = i / kDim, d = i - k * kDim;
         const double v = cb[i];
         cb64[k * kKmLd64 + d] = v;
-        cb32[k * kKmLd32 + d] = (float)v;
+        cb32[(k >> 2) * (kKmLd32 * kKmRows) + d * kKmRows + (k & 3)] = (float)v;
     }
     __syncthreads();
     for (int k = threadIdx.x; k < K; k += kKmThreads) {          // ||c_k||^2 in float64, rounded, next to c16
         double n2 = 0.0;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) n2 += cb64[k * kKmLd64 + d] * cb64[k * kKmLd64 + d];
-        cb32[k * kKmLd32 + 17] = (float)n2;
+        cb32[(k >> 2) * (kKmLd32 * kKmRows) + 18 * kKmRows + 2 * (k & 3)] = (float)n2;
+        cb32[(k >> 2) * (kKmLd32 * kKmRows) + 18 * kKmRows + 2 * (k & 3) + 1] = (float)n2;
     }
     // Cmax^2 = max_k ||c_k||^2 (fp32, rounded up) for the absolute slack of the screen
     __shared__ float s_c2[kKmThreads / 32];
@@ -118,8 +120,9 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
     const long nround = (N + stride - 1) / stride;
     for (long it = 0; it < nround; ++it) {
         const long i0 = it * stride + (long)blockIdx.x * per_round + threadIdx.x;     // vectors i0 + j * kKmThreads
-        float2 xm[kKmV][8];
-        float xm16[kKmV], slack[kKmV], m1[kKmV], m2[kKmV];
+        // xp[g][d] = (-2 x_d of vector 2g, -2 x_d of vector 2g+1): one packed lane per vector
+        float2 xp[kKmV / 2][kDim];
+        float slack[kKmV], m1[kKmV], m2[kKmV];
         int bi[kKmV];
 #pragma unroll
         for (int j = 0; j < kKmV; ++j) {
@@ -127,10 +130,12 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
             float x[kDim];
 #pragma unroll
             for (int d = 0; d < kDim; ++d) x[d] = i < N ? __ldg(data + i * kDim + d) : 0.0f;
-            // per-vector screen constants: xm = -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, rounded up
+            // per-vector screen constants: -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, rounded up
 #pragma unroll
-            for (int d = 0; d < 8; ++d) xm[j][d] = make_float2(-2.0f * x[2 * d], -2.0f * x[2 * d + 1]);
-            xm16[j] = -2.0f * x[16];
+            for (int d = 0; d < kDim; ++d) {
+                if (j & 1) xp[j >> 1][d].y = -2.0f * x[d];
+                else xp[j >> 1][d].x = -2.0f * x[d];
+            }
             float nx = 0.0f;
 #pragma unroll
             for (int d = 0; d < kDim; ++d) nx = __fmaf_ru(x[d], x[d], nx);
@@ -138,21 +143,54 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
             slack[j] = __fadd_ru(__fmul_ru(__fmul_ru(rr, rr), 7.62939453125e-6f), 1e-30f);   // 128 * 2^-24
             m1[j] = __int_as_float(0x7f800000); m2[j] = m1[j]; bi[j] = 0;
         }
-        // One divergence-free sweep keeps the two smallest screened values of every vector.  All s_k of a vector
-        // share the ||x||^2 term, so two of them compare with error <= 2 * 21 u R: if the runner-up is more than
-        // the slack above the smallest, the smallest is the exact argmin (no float64 work at all); otherwise the
-        // vector is ambiguous (near-tie, duplicate centroids) and the candidates inside the slack are decided in
-        // float64 exactly as numpy does, ascending k with strict <, i.e. first minimum.
-        for (int k = 0; k < K; ++k) {
-            const KmRow row = load_row(cb32 + k * kKmLd32);
+        // One divergence-free sweep keeps the two smallest screened values of every vector.  A step takes kKmRows
+        // centroid rows; for each dimension the packed pair of two vectors is multiplied by the broadcast scalar
+        // c[r][d] of every row in turn (fma.rn.f32x2, scalar-broadcast form: the pair operand is reused by the
+        // kKmRows consecutive instructions, which is what lets FFMA2 issue every 2 cycles), 17 packed FMAs per two
+        // (vector, centroid) pairs and nothing else.  All s_k of a vector share the ||x||^2 term, so two of them
+        // compare with error <= 2 * 19 u R: if the runner-up is more than the slack above the smallest, the smallest
+        // is the exact argmin (no float64 work at all); otherwise the vector is ambiguous (near-tie, duplicate
+        // centroids) and the candidates inside the slack are decided in float64 exactly as numpy does, ascending k
+        // with strict <, i.e. first minimum.
+        for (int k = 0; k < Kp; k += kStepRows) {
+            const float4 *blk = reinterpret_cast<const float4 *>(cb32 + k * kKmLd32);
+            float2 acc[kStepRows][kKmV / 2];
 #pragma unroll
-            for (int j = 0; j < kKmV; ++j) {
-                const float s = screen17(xm[j], xm16[j], row);
-                const bool p = s < m1[j];
-                m2[j] = fminf(m2[j], fmaxf(m1[j], s));
-                m1[j] = fminf(m1[j], s);
-                bi[j] = p ? k : bi[j];
+            for (int nb = 0; nb < kKmNB; ++nb) {
+                const float4 na = blk[nb * kKmLd32 + 18], nb4 = blk[nb * kKmLd32 + 19], c0 = blk[nb * kKmLd32];
+                const float cr[kKmRows] = {c0.x, c0.y, c0.z, c0.w};
+                const float2 cn[kKmRows] = {make_float2(na.x, na.y), make_float2(na.z, na.w), make_float2(nb4.x, nb4.y),
+                                            make_float2(nb4.z, nb4.w)};
+#pragma unroll
+                for (int g = 0; g < kKmV / 2; ++g)
+#pragma unroll
+                    for (int r = 0; r < kKmRows; ++r) acc[nb * kKmRows + r][g] = fma2(xp[g][0], cr[r], cn[r]);
             }
+#pragma unroll
+            for (int d = 1; d < kDim; ++d) {
+                float cr[kStepRows];
+#pragma unroll
+                for (int nb = 0; nb < kKmNB; ++nb) {
+                    const float4 cd = blk[nb * kKmLd32 + d];
+                    cr[nb * kKmRows] = cd.x; cr[nb * kKmRows + 1] = cd.y; cr[nb * kKmRows + 2] = cd.z; cr[nb * kKmRows + 3] = cd.w;
+                }
+#pragma unroll
+                for (int g = 0; g < kKmV / 2; ++g)
+#pragma unroll
+                    for (int r = 0; r < kStepRows; ++r) acc[r][g] = fma2(xp[g][d], cr[r], acc[r][g]);
+            }
+            // (a (lo, hi) merge tree per step with FMNMX3 needs fewer ALU instructions, but then the winning row has
+            // to be recovered after the sweep with per-thread shared-memory addresses; measured 37 % slower)
+#pragma unroll
+            for (int r = 0; r < kStepRows; ++r)
+#pragma unroll
+                for (int j = 0; j < kKmV; ++j) {
+                    const float s = (j & 1) ? acc[r][j >> 1].y : acc[r][j >> 1].x;
+                    const bool p = s < m1[j];
+                    m2[j] = fminf(m2[j], fmaxf(m1[j], s));
+                    m1[j] = fminf(m1[j], s);
+                    bi[j] = p ? k + r : bi[j];
+                }
         }
 #pragma unroll
         for (int j = 0; j < kKmV; ++j) {
@@ -169,7 +207,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                 double best = 0.0;
                 bool have = false;
                 for (int k = 0; k < K; ++k) {
-                    const float s = screen17(xm[j], xm16[j], load_row(cb32 + k * kKmLd32));
+                    const float s = screen17(x, cb32, k);
                     if (s <= thr) {
                         const double d = exact17(x, cb64 + k * kKmLd64);
                         if (!have || d < best) { best = d; bi[j] = k; have = true; }
@@ -294,12 +332,12 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     const int sms = num_sms();
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
     cudaStream_t st = (cudaStream_t)stream;
-    const size_t smem = (size_t)K * (kKmLd64 * 8 + kKmLd32 * 4);
-    static size_t configured = 0;
-    if (smem > configured) {
+    const size_t smem = (size_t)K * kKmLd64 * 8 + (size_t)((K + kKmPad - 1) / kKmPad * kKmPad) * kKmLd32 * 4;
+    static bool configured = false;
+    if (!configured) {
         FPC_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
                                           (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4))));
-        configured = (size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4);
+        configured = true;
     }
     long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;

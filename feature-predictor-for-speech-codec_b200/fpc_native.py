@@ -20,7 +20,8 @@ HIST_TOTAL = 3584
 EXPORTS = (
     "fpc_version", "fpc_status_string", "fpc_last_cuda_error", "fpc_launch_count",
     "fpc_packed_weights_bytes", "fpc_pack_weights", "fpc_packed_codebooks_bytes", "fpc_pack_codebooks",
-    "fpc_encode_workspace_bytes", "fpc_encode", "fpc_decode", "fpc_index_histogram",
+    "fpc_encode_workspace_bytes", "fpc_encode", "fpc_encode_host_workspace_bytes", "fpc_encode_host",
+    "fpc_decode", "fpc_index_histogram",
     "fpc_vq_quantize_packed", "fpc_scl_quantize",
     "fpc_kmeans_workspace_bytes", "fpc_kmeans_assign_accumulate", "fpc_kmeans_finalize", "fpc_kmeans_gather",
     "fpc_selftest_umma", "fpc_debug_set_phase_buffer", "fpc_ceps2lpc",
@@ -53,6 +54,16 @@ class EncodeIO(ctypes.Structure):
         ("d_c_in", ctypes.c_void_p), ("d_r", ctypes.c_void_p), ("d_r_qtz", ctypes.c_void_p),
         ("d_r_under", ctypes.c_void_p), ("d_ind1", ctypes.c_void_p), ("d_ind2", ctypes.c_void_p),
         ("d_idx", ctypes.c_void_p),
+    ]
+
+
+class EncodeHostIO(ctypes.Structure):
+    _fields_ = [
+        ("h_feat", ctypes.c_void_p), ("B", ctypes.c_int), ("L", ctypes.c_int),
+        ("l1", ctypes.c_float), ("l2", ctypes.c_float), ("qtz", ctypes.c_int),
+        ("h_c_in", ctypes.c_void_p), ("h_r", ctypes.c_void_p), ("h_r_qtz", ctypes.c_void_p),
+        ("h_r_under", ctypes.c_void_p), ("h_ind1", ctypes.c_void_p), ("h_ind2", ctypes.c_void_p),
+        ("h_idx", ctypes.c_void_p),
     ]
 
 
@@ -90,6 +101,9 @@ def lib():
     L.fpc_encode_workspace_bytes.restype = cs
     L.fpc_encode_workspace_bytes.argtypes = [ci, ci, ci]
     L.fpc_encode.argtypes = [vp, vp, ctypes.POINTER(EncodeIO), ci, vp, cs, vp]
+    L.fpc_encode_host_workspace_bytes.restype = cs
+    L.fpc_encode_host_workspace_bytes.argtypes = [ci, ci, ci]
+    L.fpc_encode_host.argtypes = [vp, vp, ctypes.POINTER(EncodeHostIO), ci, ci, vp, cs, vp]
     L.fpc_decode.argtypes = [vp, vp, vp, ci, ci, vp, ci, vp, cs, vp]
     L.fpc_index_histogram.argtypes = [vp, cl, vp, vp]
     L.fpc_vq_quantize_packed.argtypes = [vp, cl, vp, ci, ci, ci, vp, vp, vp]

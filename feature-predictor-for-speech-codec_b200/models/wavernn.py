@@ -162,6 +162,62 @@ class Wavernn(nn.Module):
         self.last_result = res
         return res
 
+    def encode_host(self, cfg, feat, l1, l2, qtz=True, out=None, chunks=0, device=None, want_under=False):
+        """Host-buffer form of the closed loop: what `feat.to('cuda')` -> `encoder(...)` -> `.cpu()` of the results
+        does in the reference scripts (synthesis_qtz.py:149-160, generate_qtz_features.py:55-70), as ONE call that
+        cuts the utterances along time and overlaps upload, kernel and download (C ABI fpc_encode_host).
+
+        feat: (B, L, 20) float32 CPU tensor (pinned memory lets the copies overlap).  out: optional dict of CPU
+        tensors to fill ("c_in", "r", "r_qtz", "r_under", "ind1", "ind2", "idx"); missing ones are allocated pinned
+        ("r_under" only if want_under).  Returns the dict; the tensors are complete after
+        torch.cuda.current_stream(device).synchronize().  Bit-identical to encoder() on the same input."""
+        N.require_cuda()
+        if not isinstance(feat, torch.Tensor) or feat.is_cuda:
+            raise N.FpcError("encode_host takes a CPU tensor; use encoder()/encode_device() for CUDA tensors")
+        if feat.dim() != 3 or feat.shape[2] != _GEOMETRY[0]:
+            raise ValueError("feat must be (batch, frames, 20), got %r" % (tuple(feat.shape),))
+        dev = torch.device(device) if device is not None else next(self.parameters()).device
+        if dev.type != "cuda":
+            raise N.FpcError("the model must live on a CUDA device (no CPU fallback)")
+        feat = feat.detach().to(torch.float32).contiguous()
+        B, Lf, _ = feat.shape
+        cbs = fpc_codebooks.from_cfg(cfg, dev) if qtz else None
+        if qtz and (cbs.arrays["vq"] is None or cbs.arrays["scl"] is None):
+            raise FileNotFoundError("cfg['cb_path'] and cfg['scl_cb_path'] are required when qtz is set")
+        weights = self.packed_weights(dev)
+        shapes = {"c_in": ((B, Lf, 20), torch.float32), "r": ((B, Lf, 18), torch.float32),
+                  "r_qtz": ((B, Lf, 18), torch.float32), "r_under": ((B, Lf, 18), torch.float32),
+                  "ind1": ((B, Lf, 1), torch.float32), "ind2": ((B, Lf, 1), torch.float32),
+                  "idx": ((B, Lf, 4), torch.int32)}
+        res = dict(out) if out else {}
+        for k, (shp, dt) in shapes.items():
+            if k == "r_under" and not want_under and k not in res:
+                continue
+            t = res.get(k)
+            if t is None:
+                t = torch.empty(shp, dtype=dt).pin_memory()
+            if t.is_cuda or t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
+                raise ValueError("out[%r] must be a contiguous CPU %s tensor of shape %r" % (k, dt, shp))
+            res[k] = t
+        with torch.cuda.device(dev):
+            need = N.lib().fpc_encode_host_workspace_bytes(B, Lf, self.precision)
+            ws = getattr(self, "_host_ws", None)
+            if ws is None or ws.device != dev or ws.numel() < need:
+                ws = torch.empty(max(need, 1), dtype=torch.uint8, device=dev)
+                self._host_ws = ws
+            io = N.EncodeHostIO()
+            io.h_feat = feat.data_ptr()
+            io.B, io.L = B, Lf
+            io.l1, io.l2 = float(l1), float(l2)
+            io.qtz = 1 if qtz else 0
+            for k in shapes:
+                setattr(io, "h_" + k, res[k].data_ptr() if k in res else None)
+            N.check(N.lib().fpc_encode_host(weights.data_ptr(), cbs.ptr() if cbs is not None else None,
+                                            ctypes.byref(io), self.precision, int(chunks), ws.data_ptr(), ws.numel(),
+                                            N.current_stream(dev)), "fpc_encode_host")
+        self._host_keep = (cbs, feat, weights, res)      # keep alive until the asynchronous work has run
+        return res
+
     def histograms(self, res):
         """cb_tot (wavernn.py:189,221-240): five usage tables from the index record."""
         cbs = res.codebooks[0]

@@ -151,6 +151,37 @@ size_t fpc_encode_workspace_bytes(int B, int L, int precision);
 int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_io *io,
                int precision, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* ---- host-buffer form of the closed loop ------------------------------------------------------------------------
+ * Replaces the reference's host sequence  feat.to('cuda') -> model_f.encoder(...) -> results .cpu()
+ * (synthesis_qtz.py:149-160, generate_qtz_features.py:55-70) for callers whose features and results live in host
+ * memory.  The utterances are cut along TIME into `chunks` frame ranges; the upload of range c+1, the kernel of
+ * range c (the recurrent state is carried between launches in the workspace) and the download of range c-1 run
+ * concurrently on three streams, so the PCIe copies hide behind the arithmetic.  Results are bit-identical to
+ * fpc_encode on the same inputs.  Host buffers should be pinned (cudaHostAlloc / torch pin_memory); pageable memory
+ * works but serialises the copies.  Thresholds only (no external mask).  The call is asynchronous: the results are
+ * complete when `stream` has been synchronised. */
+typedef struct fpc_encode_host_io {
+    const float *h_feat;   /* (B, L, 20) float32, host */
+    int B, L;
+    float l1, l2;
+    int qtz;
+    float *h_c_in;         /* (B, L, 20) host outputs; any of them may be NULL (not downloaded) */
+    float *h_r;            /* (B, L, 18) */
+    float *h_r_qtz;        /* (B, L, 18) */
+    float *h_r_under;      /* (B, L, 18) */
+    float *h_ind1;         /* (B, L) */
+    float *h_ind2;         /* (B, L) */
+    int32_t *h_idx;        /* (B, L, 4) */
+} fpc_encode_host_io;
+
+/* device scratch fpc_encode_host needs: the device copies of the input, of every output, and the carried state */
+size_t fpc_encode_host_workspace_bytes(int B, int L, int precision);
+
+/* chunks <= 0: chosen by the library (48+ frames per range, at most 16 ranges).  FPC_PREC_BF16 runs as one
+ * range (its kernel does not carry state between launches yet). */
+int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_host_io *io,
+                    int precision, int chunks, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* receiver side: c[t] = predictor(c[t-1]) + r_qtz[t], pitch passed through.
  * d_r_qtz (B,L,18), d_pitch (B,L,2) -> d_c_out (B,L,20). */
 int fpc_decode(const void *d_packed_weights, const float *d_r_qtz, const float *d_pitch, int B, int L,

@@ -113,6 +113,41 @@ def test_encoder_bit_exact_vs_oracle(torch_cuda, model, oracle, oracle_weights, 
     assert hist_equal(gpu["cb_tot"], oracle.histograms(ora["idx"], oracle_codebooks(oracle, cbs)))
 
 
+@pytest.mark.parametrize("B,L,chunks,pinned", [
+    (70, 40, 1, True),          # one range: plain upload -> kernel -> download
+    (70, 40, 3, True),          # ranges of unequal length (13, 13, 14 frames), ragged batch
+    (150, 37, 5, False),        # several tiles per CTA, pageable host memory
+    (33, 200, 0, True),         # library-chosen chunking
+    (5, 7, 64, True),           # more ranges asked for than frames
+])
+def test_encode_host_matches_device_path(torch_cuda, model, synth, cbdir, B, L, chunks, pinned):
+    """fpc_encode_host (time-chunked upload / kernel / download pipeline with the recurrent state carried between
+    launches) returns exactly what the device-resident call returns, for both quantised and residual mode."""
+    torch = torch_cuda
+    cbs = synth.make_codebooks(0)
+    cfg = synth.save_codebooks(cbs, os.path.join(cbdir, "host"))
+    feat = synth.make_features(B, L, first_utt=7300)
+    fh = torch.from_numpy(feat)
+    if pinned:
+        fh = fh.pin_memory()
+    for qtz, l1, l2 in ((True, 0.25, 2.1), (True, 0.09, 0.28), (False, 0.25, 2.1)):
+        ref = run_gpu(torch, model, cfg if qtz else {}, feat, l1, l2, qtz=qtz)
+        out = None
+        if not pinned:
+            out = {"c_in": torch.empty((B, L, 20)), "idx": torch.empty((B, L, 4), dtype=torch.int32)}
+        host = model.encode_host(cfg if qtz else {}, fh, l1, l2, qtz=qtz, out=out, chunks=chunks, want_under=True)
+        torch.cuda.synchronize()
+        for k in ("c_in", "r", "r_qtz", "r_under", "ind1", "ind2", "idx"):
+            assert np.array_equal(host[k].numpy(), ref[k]), "encode_host differs in %s (qtz=%s, chunks=%d)" % (k, qtz, chunks)
+    # second call reuses the workspace and the pipeline streams: still identical
+    again = model.encode_host(cfg, fh, 0.25, 2.1, chunks=chunks)
+    torch.cuda.synchronize()
+    ref = run_gpu(torch, model, cfg, feat, 0.25, 2.1)
+    assert np.array_equal(again["idx"].numpy(), ref["idx"]) and np.array_equal(again["c_in"].numpy(), ref["c_in"])
+    with pytest.raises(Exception):
+        model.encode_host(cfg, fh.cuda(), 0.25, 2.1)
+
+
 def test_residual_mode_and_masks(torch_cuda, model, oracle, oracle_weights, synth):
     feat = synth.make_features(19, 30, first_utt=7100)
     gpu = run_gpu(torch_cuda, model, {}, feat, 0.25, 2.1, qtz=False)

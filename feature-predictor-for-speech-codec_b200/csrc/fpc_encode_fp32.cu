@@ -78,13 +78,16 @@ __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], fl
 {
     constexpr int NP = kGk / 2;      // k-pairs per group
     for (int g = 0; g < ng; ++g) {
+#ifndef FPC_DEBUG_NO_STREAM          // (debug builds only, tools/gemm_bounds.sh: the arithmetic without the weight stream etc.)
         mbar_wait(&full[pp.s], pp.ph);
+#endif
         const float4 *sw = ring + pp.s * (kGroupFloats / 4) + ug;
         float4 w[3][NP];             // [gate][k-pair] = (e0,k) (e1,k) (e0,k+1) (e1,k+1)
 #pragma unroll
         for (int c = 0; c < 3; ++c)
 #pragma unroll
             for (int q = 0; q < NP; ++q) w[c][q] = sw[(c * NP + q) * 64];
+#ifndef FPC_DEBUG_STREAM_ONLY
 #pragma unroll
         for (int i = 0; i < TU; ++i) {
 #pragma unroll
@@ -107,8 +110,11 @@ __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], fl
                 ar[i] = r; az[i] = z; an[i] = n;
             }
         }
+#endif
+#ifndef FPC_DEBUG_NO_STREAM
         __syncwarp();
         if (lane == 0) mbar_arrive(&empty[pp.s]);
+#endif
         pp.advance();
     }
 }
@@ -190,7 +196,12 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
             const char *src = reinterpret_cast<const char *>(P.wstream) + (size_t)(blockIdx.x % kWeightReplicas) * kPackedF32ReplicaBytes;
             int s = 0, gf = 0;
             uint32_t wraps = 0;
-            for (long long g = 0; g < total; ++g) {
+#ifdef FPC_DEBUG_NO_STREAM
+            const long long ntotal = 0 * total;
+#else
+            const long long ntotal = total;
+#endif
+            for (long long g = 0; g < ntotal; ++g) {
                 if (wraps > 0) mbar_wait(&empty[s], (wraps - 1) & 1u);
                 mbar_arrive_expect_tx(&full[s], kGroupBytes);
                 bulk_g2s(smem + S::offRing + s * kGroupBytes, src + (size_t)gf * kGroupBytes, kGroupBytes, &full[s]);

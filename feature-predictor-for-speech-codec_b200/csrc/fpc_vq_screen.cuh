@@ -135,15 +135,18 @@ __device__ __forceinline__ void upd2(float &m1, int &i1, float &m2, float v, int
     i1 = p ? idx : i1;
 }
 
-// Every one of the 256 compute threads must call this with identical arguments (barrier id 1).
-// scratch_bytes >= screen_fixed_bytes(maxn) + 4096 and large enough for the exact fallback
-// (vq_fixed_bytes<T>(8) + 1024 * sizeof(T)).
-template <typename T>
+// Every one of the NT (256 or 128) compute threads must call this with identical arguments (barrier id 1).
+// scratch_bytes >= screen_fixed_bytes(maxn) + 8192 and large enough for the exact fallback
+// (vq_fixed_bytes<T>(8) + 1024 * sizeof(T)).  A thread covers the codebook in NSUB = 512 / NT sub-passes of two
+// codewords; NSUB * (NT / 32) = 16 partial results per vector either way.
+template <typename T, int NT = kComputeThreads>
 __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, const char *__restrict__ cbbase, const int *__restrict__ list,
                                         int n, int maxn, const float *__restrict__ rs, float *__restrict__ rq,
                                         int *__restrict__ idx1, int *__restrict__ idx2, char *__restrict__ scratch,
                                         int scratch_bytes, int tid, T *__restrict__ qglobal = nullptr, long long *dbg = nullptr)
 {
+    constexpr int NW = NT / 32, NSUB = 512 / NT;
+    static_assert(NT == 256 || NT == 128, "block-wide search is written for 256 or 128 threads");
     const int warp = tid >> 5, lane = tid & 31;
     // The header is re-read here on every call (volatile): its fields are loop-invariant for the
     // frame loop of the fused kernels, and left to itself the compiler hoists a dozen 64-bit offsets
@@ -188,7 +191,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
 #pragma unroll
         for (int d = 0; d < kDim; ++d) xm2[tid * 20 + d] = -2.0f * xr[d];      // exact (power of two)
     }
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
     FPC_VQT(2);
 
     Cw2 w;
@@ -199,8 +202,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
         for (int base = 0; base < n; base += vb) {
             const int nb = min(vb, n - base);
 #pragma unroll 1
-            for (int h = 0; h < 2; ++h) {
-                const int k = 2 * tid + 512 * h;
+            for (int h = 0; h < NSUB; ++h) {
+                const int k = 2 * tid + 2 * NT * h;
                 const bool act = k < Kp;
                 if (act) load_cw2(w, cf, nf, Kp, k);
                 for (int v = 0; v < nb; v += 2) {
@@ -217,14 +220,15 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                     if (v + 1 < nb) *reinterpret_cast<uint2 *>(keybuf + (v + 1) * 1024 + k) = kc;
                 }
             }
-            named_bar_sync(1, kComputeThreads);
+            named_bar_sync(1, NT);
             FPC_VQT(3);
-            if (warp < nb) {
-                const int v = base + warp;
+#pragma unroll 1
+            for (int vw = warp; vw < nb; vw += NW) {
+                const int v = base + vw;
                 unsigned t0 = 0xffffffffu, t1 = 0xffffffffu, t2 = 0xffffffffu, t3 = 0xffffffffu;
 #pragma unroll 2
                 for (int i = 0; i < 8; ++i) {
-                    const uint4 kk = reinterpret_cast<const uint4 *>(keybuf + warp * 1024)[i * 32 + lane];
+                    const uint4 kk = reinterpret_cast<const uint4 *>(keybuf + vw * 1024)[i * 32 + lane];
                     ins4(t0, t1, t2, t3, kk.x); ins4(t0, t1, t2, t3, kk.y); ins4(t0, t1, t2, t3, kk.z); ins4(t0, t1, t2, t3, kk.w);
                 }
                 unsigned g[8];
@@ -288,7 +292,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 }
                 if (lane == 0 && !ok) flag[v] = 1;
             }
-            named_bar_sync(1, kComputeThreads);
+            named_bar_sync(1, NT);
             FPC_VQT(4);
         }
     }
@@ -301,8 +305,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
         const float *G = reinterpret_cast<const float *>(cbbase + bk.off_g);
         const int ns = two ? kSurv : 1;
 #pragma unroll 1
-        for (int h = 0; h < 2; ++h) {
-            const int k = 2 * tid + 512 * h;
+        for (int h = 0; h < NSUB; ++h) {
+            const int k = 2 * tid + 2 * NT * h;
             const bool act = k < Kp;
             if (act) load_cw2(w, cf, nf, Kp, k);
             // Gram rows (2 vectors x 5 survivors, one float2 each) are fetched a whole vector pair ahead into
@@ -338,8 +342,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                         }
                     }
                 }
-                warp_top2_store(ma1, ia, ma2, lane, &part[va * 16 + h * 8 + warp]);
-                if (v + 1 < n) warp_top2_store(mc1, ic, mc2, lane, &part[vc * 16 + h * 8 + warp]);
+                warp_top2_store(ma1, ia, ma2, lane, &part[va * 16 + h * NW + warp]);
+                if (v + 1 < n) warp_top2_store(mc1, ic, mc2, lane, &part[vc * 16 + h * NW + warp]);
             };
             for (int v = 0; v < n; v += 4) {
                 if (ld && v + 2 < n) gram_load(gy, Gk, goff, v + 2, min(v + 3, n - 1));
@@ -350,7 +354,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 }
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         FPC_VQT(5);
         if (tid < n && !flag[tid]) {
             const int v = tid;
@@ -371,14 +375,14 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                 flag[v] = 1;
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
     }
 
     // ---- quantised vectors of the decided rows: csum = 0; csum += CB[i][index[i,0]]  (vq_func.py:127-129) ----
     {
         const T *cbr0 = reinterpret_cast<const T *>(cbbase + bk.off_r[0]);
         const T *cbr1 = reinterpret_cast<const T *>(cbbase + bk.off_r[1]);
-        for (int e = tid; e < n * kDim; e += kComputeThreads) {
+        for (int e = tid; e < n * kDim; e += NT) {
             const int v = e / kDim, d = e - v * kDim;
             if (!flag[v]) {
                 const int row = list[v];
@@ -399,7 +403,7 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
             }
             if (lane == 0) cnt[0] = nf2;
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
     }
 
     // ---- exact search for the undecided rows ----
@@ -409,30 +413,31 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
     if (nflag > 0) {
         // the row list must survive the fallback, which reuses the scratch: keep it in registers
         int mine = tid < nflag ? flist[tid] : 0;
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         int sb = 32;
         while (sb > 8 && (int)vq_fixed_bytes<T>(sb) + 1024 * (int)sizeof(T) + 4 * maxn > scratch_bytes) sb >>= 1;
         int *keep = reinterpret_cast<int *>(scratch + scratch_bytes - 4 * maxn);   // tail of the scratch: the list
         if (tid < nflag) keep[tid] = mine;
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         int vbe = (scratch_bytes - 4 * maxn - (int)vq_fixed_bytes<T>(sb)) / (1024 * (int)sizeof(T));
         vbe = vbe > 8 ? 8 : vbe;
         for (int off = 0; off < nflag; off += sb)
-            vq_search_rows<T>(bk, cbbase, keep + off, min(sb, nflag - off), sb, rs, rq, idx1, idx2, scratch, vbe, tid, qglobal);
+            vq_search_rows<T, NT>(bk, cbbase, keep + off, min(sb, nflag - off), sb, rs, rq, idx1, idx2, scratch, vbe, tid, qglobal);
         FPC_VQT(7);
     }
 #undef FPC_VQT
 }
 
 // dtype dispatch used by the fused frame-step kernels
+template <int NT = kComputeThreads>
 __device__ __forceinline__ void vq_dispatch_screened(const PackedVq &bk, const char *cbbase, const int *list, int n, int maxn,
                                                      const float *rs, float *rq, int *idx1, int *idx2, char *scratch,
                                                      int scratch_bytes, int tid, long long *dbg = nullptr)
 {
     if (bk.dtype == FPC_F32)
-        vq_search_rows_screened<float>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
+        vq_search_rows_screened<float, NT>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
     else
-        vq_search_rows_screened<double>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
+        vq_search_rows_screened<double, NT>(bk, cbbase, list, n, maxn, rs, rq, idx1, idx2, scratch, scratch_bytes, tid, nullptr, dbg);
 }
 
 }  // namespace fpc

@@ -22,12 +22,13 @@ template <typename T> __host__ __device__ constexpr size_t vq_fixed_bytes(int ma
     return (size_t)5 * maxn * 20 * sizeof(T) + (size_t)5 * maxn * 8 * sizeof(VqPart<T>) + (size_t)((maxn * 5 * 4 + 15) / 16) * 16;
 }
 
-template <typename T>
-__device__ __forceinline__ void load_codewords(T (&cw)[4][kDim], const T *__restrict__ cbt, int K, int tid)
+// thread t of NT owns codewords t + NT * s, s = 0 .. 1024/NT - 1, held four slots (one "chunk") at a time
+template <typename T, int NT>
+__device__ __forceinline__ void load_codewords(T (&cw)[4][kDim], const T *__restrict__ cbt, int K, int tid, int ch)
 {
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        const int c = tid + 256 * q;
+        const int c = tid + NT * (4 * ch + q);
 #pragma unroll
         for (int d = 0; d < kDim; ++d) cw[q][d] = c < K ? cbt[(size_t)d * K + c] : (T)0;
     }
@@ -46,16 +47,16 @@ __device__ __forceinline__ void load_row_vector(T (&x)[kDim], const float *__res
 
 // nearest codeword of `x` among this thread's codewords, merged across the warp; lane 0
 // records the warp's (distance, index) pair
-template <typename T>
-__device__ __forceinline__ void search_own(const T (&x)[kDim], const T (&cw)[4][kDim], int nq, int K, int tid,
+template <typename T, int NT>
+__device__ __forceinline__ void search_own(const T (&x)[kDim], const T (&cw)[4][kDim], int nq, int K, int tid, int ch,
                                            VqPart<T> *__restrict__ out)
 {
     T bd = Rn<T>::inf();
     int bi = 0x7fffffff;
 #pragma unroll
     for (int q = 0; q < 4; ++q) {
-        if (q < nq) {
-            const int c = tid + 256 * q;
+        if (4 * ch + q < nq) {
+            const int c = tid + NT * (4 * ch + q);
             const T d = dist17<T>(x, cw[q]);
             if (c < K && (d < bd || bi == 0x7fffffff)) { bd = d; bi = c; }
         }
@@ -64,7 +65,7 @@ __device__ __forceinline__ void search_own(const T (&x)[kDim], const T (&cw)[4][
     if ((tid & 31) == 0) { out->d = bd; out->i = bi; }
 }
 
-// merge the 8 per-warp partial results of one search; all lanes return the winner
+// merge the 8 partial results (warps x chunks) of one search; all lanes return the winner
 template <typename T>
 __device__ __forceinline__ void merge_parts(const VqPart<T> *__restrict__ p, int lane, T &bd, int &bi)
 {
@@ -83,15 +84,18 @@ __device__ __forceinline__ void merge_parts(const VqPart<T> *__restrict__ p, int
 //   scratch: vq_fixed_bytes<T>(maxn) + vb*1024*sizeof(T) bytes, vb >= 1
 // Every thread of the 256 must call this with identical arguments (barrier id 1 is used).
 // ------------------------------------------------------------------------------------------
-template <typename T>
+template <typename T, int NT = kComputeThreads>
 __device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__restrict__ cbbase, const int *__restrict__ list, int n,
                                int maxn, const float *__restrict__ rs, float *__restrict__ rq, int *__restrict__ idx1,
                                int *__restrict__ idx2, char *__restrict__ scratch, int vb, int tid,
                                T *__restrict__ qglobal = nullptr)
 {
+    constexpr int NW = NT / 32;            // warps
+    constexpr int NCH = 256 / NT;          // chunks of four codeword slots per thread (NW * NCH = 8 partials per search)
+    static_assert(NT == 256 || NT == 128, "block-wide search is written for 256 or 128 threads");
     const int warp = tid >> 5, lane = tid & 31;
     const int K = bk.K;
-    const int nq = (K + 255) >> 8;   // codeword slots per thread in use
+    const int nq = (K + NT - 1) / NT;   // codeword slots per thread in use
     const T *cbt0 = reinterpret_cast<const T *>(cbbase + bk.off_t[0]);
     const T *cbr0 = reinterpret_cast<const T *>(cbbase + bk.off_r[0]);
     T *dl = reinterpret_cast<T *>(scratch);
@@ -100,16 +104,19 @@ __device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__re
     T *dbuf = reinterpret_cast<T *>(scratch + vq_fixed_bytes<T>(maxn));
 
     T cw[4][kDim];
-    load_codewords<T>(cw, cbt0, K, tid);
 
     if (bk.stages == 1) {
-        for (int v = 0; v < n; ++v) {
-            T x[kDim];
-            load_row_vector<T>(x, rs + list[v] * kLdR + 4);
-            search_own<T>(x, cw, nq, K, tid, &part[v * 8 + warp]);
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_codewords<T, NT>(cw, cbt0, K, tid, ch);
+            for (int v = 0; v < n; ++v) {
+                T x[kDim];
+                load_row_vector<T>(x, rs + list[v] * kLdR + 4);
+                search_own<T, NT>(x, cw, nq, K, tid, ch, &part[v * 8 + ch * NW + warp]);
+            }
         }
-        named_bar_sync(1, kComputeThreads);
-        for (int v = warp; v < n; v += 8) {
+        named_bar_sync(1, NT);
+        for (int v = warp; v < n; v += NW) {
             T bd; int bi;
             merge_parts<T>(&part[v * 8], lane, bd, bi);
             const int row = list[v];
@@ -120,29 +127,32 @@ __device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__re
             }
             if (lane == 0) { idx1[row] = bi; idx2[row] = -1; }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         return;
     }
 
     // ---- stage 0: distances to all K entries, 5 best per vector, stage-1 search vectors ----
     for (int base = 0; base < n; base += vb) {
         const int nb = min(vb, n - base);
-        for (int v = 0; v < nb; ++v) {
-            T x[kDim];
-            load_row_vector<T>(x, rs + list[base + v] * kLdR + 4);
+#pragma unroll 1
+        for (int ch = 0; ch < NCH; ++ch) {
+            load_codewords<T, NT>(cw, cbt0, K, tid, ch);
+            for (int v = 0; v < nb; ++v) {
+                T x[kDim];
+                load_row_vector<T>(x, rs + list[base + v] * kLdR + 4);
 #pragma unroll
-            for (int q = 0; q < 4; ++q) {
-                if (q < nq) {
-                    const int c = tid + 256 * q;
-                    const T d = dist17<T>(x, cw[q]);
-                    dbuf[v * 1024 + c] = c < K ? d : Rn<T>::inf();
+                for (int q = 0; q < 4; ++q) {
+                    if (4 * ch + q < nq) {
+                        const int c = tid + NT * (4 * ch + q);
+                        const T d = dist17<T>(x, cw[q]);
+                        dbuf[v * 1024 + c] = c < K ? d : Rn<T>::inf();
+                    }
                 }
             }
         }
-        named_bar_sync(1, kComputeThreads);
-        if (warp < nb) {
-            const int v = warp;
-            const int nj = nq * 8;
+        named_bar_sync(1, NT);
+        for (int v = warp; v < nb; v += NW) {
+            const int nj = (nq * NT) >> 5;
             T loc[32];
 #pragma unroll
             for (int j = 0; j < 32; ++j) loc[j] = j < nj ? dbuf[v * 1024 + lane + 32 * j] : Rn<T>::inf();
@@ -169,23 +179,26 @@ __device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__re
                 }
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
     }
 
     // ---- stage 1: nearest entry for every (vector, survivor) pair ----
     const T *cbt1 = reinterpret_cast<const T *>(cbbase + bk.off_t[1]);
     const T *cbr1 = reinterpret_cast<const T *>(cbbase + bk.off_r[1]);
-    load_codewords<T>(cw, cbt1, K, tid);
-    for (int p = 0; p < n * kSurv; ++p) {
-        const T *xr = dl + p * 20;
-        T x[kDim];
+#pragma unroll 1
+    for (int ch = 0; ch < NCH; ++ch) {
+        load_codewords<T, NT>(cw, cbt1, K, tid, ch);
+        for (int p = 0; p < n * kSurv; ++p) {
+            const T *xr = dl + p * 20;
+            T x[kDim];
 #pragma unroll
-        for (int d = 0; d < kDim; ++d) x[d] = xr[d];
-        search_own<T>(x, cw, nq, K, tid, &part[p * 8 + warp]);
+            for (int d = 0; d < kDim; ++d) x[d] = xr[d];
+            search_own<T, NT>(x, cw, nq, K, tid, ch, &part[p * 8 + ch * NW + warp]);
+        }
     }
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
     // ---- merge: strict < across survivor ranks keeps the earlier rank on ties (:115-125) ----
-    for (int v = warp; v < n; v += 8) {
+    for (int v = warp; v < n; v += NW) {
         T fd = Rn<T>::inf();
         int fs = 0, fi = 0;
         for (int s = 0; s < kSurv; ++s) {
@@ -203,7 +216,7 @@ __device__ __noinline__ void vq_search_rows(const PackedVq &bk, const char *__re
         }
         if (lane == 0) { idx1[row] = i0; idx2[row] = fi; }
     }
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
 }
 
 // scratch_bytes is what the caller really has; vb (vectors per stage-0 batch) follows from it

@@ -17,14 +17,14 @@ if bf16:
 d = tempfile.mkdtemp(); cfg = S.save_codebooks(S.make_codebooks(0), d)
 base = S.make_features(min(U, 256), L)
 feat = torch.from_numpy(np.tile(base, ((U + len(base) - 1) // len(base), 1, 1))[:U]).cuda()
-buf = torch.zeros(16 * 148, dtype=torch.int64, device="cuda")
+buf = torch.zeros(16 * 1024, dtype=torch.int64, device="cuda")     # one row of 16 counters per CTA
 with torch.no_grad():
     m.encode_device(cfg, feat, None, l1, l2); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); res = m.encode_device(cfg, feat, None, l1, l2); e1.record(); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(None)
-c = buf.cpu().numpy().astype(np.float64).reshape(148, 16)
+c = buf.cpu().numpy().astype(np.float64).reshape(-1, 16)
 c = c[c[:, 5] > 0]
 fr = c[:, 5:6]
 names = ["gru", "fc+residual", "thresholds+scalar", "vq", "feedback/out"]

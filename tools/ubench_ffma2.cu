@@ -130,6 +130,45 @@ __global__ void gemm_block(float *out, long long *cycles, const float4 *src)
     if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
 }
 
+// dependent-issue latency: NCH independent chains, each instruction depends on the one NCH before it; fully unrolled
+template <int NCH, bool PACKED>
+__global__ void latency(float *out, long long *cycles, float s0, float s1)
+{
+    float2 acc[NCH];
+    for (int i = 0; i < NCH; ++i) acc[i] = make_float2(threadIdx.x * 1e-3f + i, i * 0.5f);
+    const float2 w = make_float2(s0, s1);
+    __syncthreads();
+    const long long t0 = clock64();
+#pragma unroll 1
+    for (int it = 0; it < 64; ++it) {
+#pragma unroll
+        for (int u = 0; u < 64; ++u) {
+#pragma unroll
+            for (int i = 0; i < NCH; ++i) {
+                if (PACKED) acc[i] = fma2b(w, s1, acc[i]);
+                else acc[i].x = fmaf(s0, s1, acc[i].x);
+            }
+        }
+    }
+    const long long t1 = clock64();
+    float r = 0.f;
+    for (int i = 0; i < NCH; ++i) r += acc[i].x + acc[i].y;
+    out[threadIdx.x] = r;
+    if (threadIdx.x == 0 && blockIdx.x == 0) *cycles = t1 - t0;
+}
+template <int NCH, bool PACKED>
+void run_latency()
+{
+    float *out; long long *cyc, h;
+    cudaMalloc(&out, 1024 * 4); cudaMalloc(&cyc, 8);
+    latency<NCH, PACKED><<<1, 32>>>(out, cyc, 1.0001f, 0.9999f);
+    cudaDeviceSynchronize();
+    cudaMemcpy(&h, cyc, 8, cudaMemcpyDeviceToHost);
+    printf("%s, %2d independent chains, one warp: %.2f cycles per instruction -> chain step every %.1f cycles\n",
+           PACKED ? "FFMA2" : "FFMA ", NCH, (double)h / (64.0 * 64 * NCH), (double)h / (64.0 * 64));
+    cudaFree(out); cudaFree(cyc);
+}
+
 template <int ORDER>
 void run_block(const char *name, int warps_per_sched)
 {
@@ -181,6 +220,8 @@ int main()
         run_block<0>("GEMM block, rows innermost", w);
         run_block<1>("GEMM block, gates innermost", w);
     }
+    run_latency<1, true>(); run_latency<2, true>(); run_latency<4, true>(); run_latency<8, true>(); run_latency<16, true>();
+    run_latency<1, false>(); run_latency<2, false>(); run_latency<4, false>(); run_latency<8, false>();
     run<2, 1>("FFMA2 dependent chain", 1);
     run<2, 2>("FFMA2 2 chains", 1);
     run<2, 4>("FFMA2 4 chains", 1);

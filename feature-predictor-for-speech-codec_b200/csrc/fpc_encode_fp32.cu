@@ -9,7 +9,7 @@
 //
 // Work split inside a CTA (384 threads = 3 warpgroups; setmaxnreg moves the producer group's
 // registers to the two compute groups):
-//   warps 0..7  compute.  Thread (tg = lane>>3, ug = warp*8 + (lane&7)) owns hidden units
+//   warps 0..7  compute.  Thread (tg = warp>>1, ug = (warp&1)*32 + lane) owns hidden units
 //               {2ug, 2ug+1} (+128*pass) for utterances {tg, tg+4, ..., tg+4(TU-1)} of the tile,
 //               i.e. a TU x 2 x {r,z,n_i,n_h} register tile; every dot product is one
 //               ascending-k FFMA chain (the canonical order the oracle follows).
@@ -67,9 +67,11 @@ struct Pipe {
 
 // ------------------------------------------------------------------------------------------
 // one "part" of a pass: NG groups of 4 k, accumulating into r, z and the third gate (n_i or n_h)
-// (Two software-pipelined variants -- weight tile of group g+1 prefetched into a second register
-// buffer, barrier probed two groups ahead -- measured 20-25 % SLOWER on B200 than this plain loop:
-// 392 k vs 316 k cycles per frame for the GRU stage; ptxas schedules the simple form better.)
+// (Measured and rejected on the B200: weight tile of group g+1 prefetched into a second register buffer, barrier
+// probed two groups ahead, whole 4-k chunks prefetched with the rows innermost, two groups per barrier round trip,
+// two half-size CTAs per SM -- all equal or slower than this plain loop; ptxas orders loads and FMAs by operand
+// readiness whatever the source says.  tools/gemm_bounds.sh: the weight stream alone needs 51 k cycles per frame,
+// the arithmetic alone 214 k of the 223 k the stage takes.)
 // ------------------------------------------------------------------------------------------
 template <int TU>
 __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], float2 (&an)[TU], int ng,
@@ -214,8 +216,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
 
     // ---------------- compute warps ----------------
     asm volatile("setmaxnreg.inc.sync.aligned.u32 232;");
-    const int tg = lane >> 3;
-    const int ug = warp * 8 + (lane & 7);
+    // Row group per WARP, unit pair per lane: the activation loads of the gate GEMM are then full-warp broadcasts
+    // (one shared-memory wavefront instead of two) and a weight LDS.128 reads 512 distinct bytes.  The GEMM needs
+    // 48 + 14 wavefronts per k step against 84 FP32-pipe cycles; with row groups inside the warp it was 48 + 28.
+    const int tg = warp >> 1;
+    const int ug = (warp & 1) * 32 + lane;
     const PackedCodebooks *cbh = reinterpret_cast<const PackedCodebooks *>(P.cb);
 
     // constants resident for the whole kernel

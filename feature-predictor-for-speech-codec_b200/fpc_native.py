@@ -25,6 +25,8 @@ EXPORTS = (
     "fpc_vq_quantize_packed", "fpc_scl_quantize",
     "fpc_kmeans_workspace_bytes", "fpc_kmeans_assign_accumulate", "fpc_kmeans_finalize", "fpc_kmeans_gather",
     "fpc_selftest_umma", "fpc_debug_set_phase_buffer", "fpc_ceps2lpc",
+    "fpc_compact_workspace_bytes", "fpc_compact_rows", "fpc_kmeans_stage_residual",
+    "fpc_dequantize", "fpc_pack_frames", "fpc_unpack_frames",
 )
 
 
@@ -116,6 +118,13 @@ def lib():
     L.fpc_selftest_umma.argtypes = [vp, vp, ci, ci, vp, vp]
     L.fpc_debug_set_phase_buffer.argtypes = [vp]
     L.fpc_ceps2lpc.argtypes = [vp, cl, ci, vp, vp, vp, vp]
+    L.fpc_compact_workspace_bytes.restype = cs
+    L.fpc_compact_workspace_bytes.argtypes = [cl]
+    L.fpc_compact_rows.argtypes = [vp, cl, ci, ci, ci, vp, vp, vp, cs, vp]
+    L.fpc_kmeans_stage_residual.argtypes = [vp, ci, vp, vp, cl, vp, vp]
+    L.fpc_dequantize.argtypes = [vp, vp, cl, vp, vp]
+    L.fpc_pack_frames.argtypes = [vp, cl, vp, vp]
+    L.fpc_unpack_frames.argtypes = [vp, vp, cl, vp, vp]
     _lib = L
     return L
 

@@ -19,6 +19,10 @@
  *   fpc_kmeans_finalize        <- quantization/cb_func.py:88-97    divide, cluster statistics
  *   fpc_kmeans_gather          <- quantization/cb_func.py:103-112  quantize
  *   fpc_ceps2lpc               <- ceps2lpc/ceps2lpc_vct.py:122-162 ceps2lpc_v
+ *   fpc_compact_rows           <- train_cb.py:177-187              training sets from the qtz=False outputs
+ *   fpc_kmeans_stage_residual  <- train_cb.py:199-200,210-211      r = quantize(cb, r) - r for the next stage
+ *   fpc_dequantize, fpc_pack_frames, fpc_unpack_frames  (no counterpart: the reference has no working receiver,
+ *                                 models/wavernn.py:367-379, and defines no bitstream)
  *
  * Conventions
  *   - Plain C: pointers, sizes, a stream handle.  No torch / C++ types cross this boundary.
@@ -228,6 +232,36 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
                         double *d_stats, void *stream);
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Codebook-training data path (train_cb.py:141-211), on the device.
+ * fpc_compact_rows keeps, in order, the rows of a (n_rows, src_stride) float32 array whose columns
+ * [col0, col0+ncols) do not sum (in absolute value) to zero, and writes those columns densely:
+ *   vector set  train_cb.py:187   r = [r[i] for i in range(len(r)) if sum(abs(r[i])) != 0]   (col0 = 1, ncols = 17)
+ *   scalar set  train_cb.py:177   [k for k in r[:,:,0].flatten() if k != 0]                   (col0 = 0, ncols = 1)
+ * d_dst must hold n_rows * ncols floats; *d_count (device) receives the number of rows kept.
+ * ------------------------------------------------------------------------------------------- */
+size_t fpc_compact_workspace_bytes(long n_rows);
+int fpc_compact_rows(const float *d_src, long n_rows, int src_stride, int col0, int ncols, float *d_dst,
+                     long long *d_count, void *d_workspace, size_t workspace_bytes, void *stream);
+/* next[i] = (float)(cb[idx[i]] - data[i]) -- the next stage's training vectors (train_cb.py:200,211; the sign is the
+ * reference's, flipped relative to the encoder's x - csum) */
+int fpc_kmeans_stage_residual(const double *d_cb, int K, const int32_t *d_idx, const float *d_data, long N,
+                              float *d_next, void *stream);
+
+/* ---------------------------------------------------------------------------------------------
+ * Receiver side and wire format of the index record idx (n_frames, 4) that fpc_encode writes.
+ * fpc_dequantize rebuilds r_qtz (n_frames, 18) from the record, bit-identical to the encoder's own r_qtz
+ * (scalar table entry for c0; csum = 0 + CB0[i1] (+ CB1[i2]) in the codebook dtype, cast to float32);
+ * fpc_dequantize + fpc_decode is the decoder.
+ * fpc_pack_frames / fpc_unpack_frames: one 32-bit word per frame -- bit 0 ind1, bit 1 ind2, bits 2-9 scalar index,
+ * bits 10-19 VQ index (stage 1 / below book), bits 20-29 VQ stage-2 index.  -1 entries ("nothing coded") are
+ * restored from the codebook set, which both sides share.
+ * ------------------------------------------------------------------------------------------- */
+int fpc_dequantize(const void *d_packed_codebooks, const int32_t *d_idx, long n_frames, float *d_r_qtz, void *stream);
+int fpc_pack_frames(const int32_t *d_idx, long n_frames, uint32_t *d_words, void *stream);
+int fpc_unpack_frames(const void *d_packed_codebooks, const uint32_t *d_words, long n_frames, int32_t *d_idx,
+                      void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * self-test of the tensor-core plumbing (tcgen05.mma / TMEM) the bf16 predictor is built on:

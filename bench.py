@@ -467,12 +467,31 @@ def bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, 
             barrier()
             launches = fpc_native.launch_count() - n0
             p1, p2 = float(res.ind1.mean().item()), float(res.ind2.mean().item())
+            ms_res = e0.elapsed_time(e1)
+            # end to end with host buffers (Wavernn.encode_host): upload, closed loop, download of every output
+            shapes = {k: (tuple(v.shape), v.dtype) for k, v in out.items()}
+            del out, res
+            feat_h = feat.cpu().pin_memory()
+            host_out = {k: torch.empty(shp, dtype=dt).pin_memory() for k, (shp, dt) in shapes.items()}
+            model.encode_host(cfg, feat_h, l1, l2, qtz=True, out=host_out, chunks=args.e2e_chunks)
+            barrier()
+            e2, e3 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            e2.record(stream)
+            for _ in range(args.bf16_steps):
+                model.encode_host(cfg, feat_h, l1, l2, qtz=True, out=host_out, chunks=args.e2e_chunks)
+            e3.record(stream)
+            barrier()
+            ms_e2e = e2.elapsed_time(e3)
+            d2h = int(sum(v.numel() * v.element_size() for v in host_out.values()))
+            h2d = int(feat_h.numel() * 4)
+            del host_out, feat_h
     finally:
         model.precision = prev
-    t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_res, ms_e2e], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms = float(t.item()) / args.bf16_steps
+    ms = float(t[0].item()) / args.bf16_steps
+    ms_e2e = float(t[1].item()) / args.bf16_steps
     pk, _ = peaks()
     fq = flops_per_frame(p1, p2) - F_GRU
     fp32_peak = 148 * 128 * 2 * pk["sm_max_mhz"] * 1e6 / 1e12
@@ -480,6 +499,8 @@ def bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, 
     return {"workload": "closed-loop encode, %d utterances x %d frames per GPU (BASELINE.json configs[2]), bf16 predictor on "
                         "tcgen05, bf16 recurrent state, exact fp32 quantisers" % (U, L),
             "value": per_gpu * world, "unit": UNIT, "ms_per_step": ms, "steps": args.bf16_steps, "gpu_launches": int(launches),
+            "e2e": {"value": U * L * world / (ms_e2e * 1e-3), "unit": UNIT, "ms_per_step": ms_e2e,
+                    "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h, "call": "Wavernn.encode_host (fpc_encode_host)"},
             "above_threshold_fraction": {"c0": p1, "c1_17": p2},
             "roofline": {"bound": "fp32", "what": "quantiser work (direct-form VQ + scalar) on the FP32 pipe",
                          "achieved": per_gpu * fq / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",

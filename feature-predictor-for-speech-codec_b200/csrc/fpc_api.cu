@@ -158,7 +158,7 @@ size_t fpc_encode_host_workspace_bytes(int B, int L, int precision)
     if (B <= 0 || L <= 0) return 0;
     size_t total = 0;
     for (int i = 0; i < 8; ++i) total += align256((size_t)B * L * kHostWords[i] * 4);
-    if (precision == FPC_PREC_FP32) total += align256(encode_fp32_state_bytes(B));
+    total += align256(precision == FPC_PREC_FP32 ? encode_fp32_state_bytes(B) : encode_bf16_state_bytes(B));
     return total;
 }
 
@@ -175,13 +175,12 @@ int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks
     if (!d_workspace || workspace_bytes < fpc_encode_host_workspace_bytes(B, L, precision)) return FPC_ERR_WORKSPACE;
     if (chunks <= 0) chunks = L / 48 < 1 ? 1 : (L / 48 > 16 ? 16 : L / 48);
     if (chunks > L) chunks = L;
-    if (precision != FPC_PREC_FP32) chunks = 1;
     if (chunks > 64) chunks = 64;
 
     char *ws = (char *)d_workspace;
     void *dev[8];
     for (int i = 0; i < 8; ++i) { dev[i] = ws; ws += align256((size_t)B * L * kHostWords[i] * 4); }
-    float *state = precision == FPC_PREC_FP32 ? (float *)ws : nullptr;
+    void *state = ws;
     void *host_out[8] = {nullptr, io->h_c_in, io->h_r, io->h_r_qtz, io->h_r_under, io->h_ind1, io->h_ind2, io->h_idx};
 
     int devid = 0;

@@ -19,7 +19,7 @@ struct EncodeParams {
     float l1, l2;
     int ntiles;
     int f0, f1;             // frame range of this launch, [f0, f1) within L (whole utterance: 0, L)
-    float *state;           // per-tile recurrent state carried between launches of consecutive ranges, or null
+    void *state;            // per-tile recurrent state carried between launches of consecutive ranges, or null
     long long *prof;        // optional debug buffer: per-phase cycle totals of CTA 0 (fpc_debug_set_phase_buffer)
 };
 
@@ -28,6 +28,7 @@ size_t encode_fp32_state_bytes(int B);   // size of EncodeParams::state for a ba
 // bf16 tensor-core predictor (fpc_encode_bf16.cu); wstream then points at the bf16 image
 int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu);
 size_t packed_bf16_bytes();
+size_t encode_bf16_state_bytes(int B);
 int pack_weights_bf16(const fpc_weights *w, void *d_packed, cudaStream_t st);
 int num_sms();
 extern long long *g_phase_buffer;   // device pointer or null

@@ -228,7 +228,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
         // 256 x 216 + 128 x 64 = 63 488 <= 384 x 168 (the launch allocation): the increase can always be granted
         asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
         if (warp == kComputeThreads / 32 && lane == 0) {
-            const long long total = (long long)my_tiles * P.L * kBStepsPerFrame;
+            const long long total = (long long)my_tiles * (P.f1 - P.f0) * kBStepsPerFrame;
             const char *src = reinterpret_cast<const char *>(P.wstream);
             int s = 0, gf = 0;
             uint32_t wraps = 0;
@@ -248,7 +248,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             uint32_t ph = 0, n_act = 0, n_acc = 0;
             for (int tile = 0; tile < my_tiles; ++tile) {
                 int cur = 0;
-                for (int fr = 0; fr < P.L; ++fr) {
+                for (int fr = P.f0; fr < P.f1; ++fr) {
                     // ---- GRU 1: three passes of 128 hidden units ----
                     mbar_wait(act_ready, n_act & 1u); ++n_act;
                     for (int pass = 0; pass < 3; ++pass) {
@@ -314,14 +314,21 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
         const int b0 = tile * NU;
         int cur = 0;
         // h1 = h2 = None -> zeros, frame 0 input all zero (wavernn.py:177-178,189)
-        for (int i = tid; i < S::kX1Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(x1[0])[i] = make_int4(0, 0, 0, 0);
-        for (int i = tid; i < S::kH2Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(h2t)[i] = make_int4(0, 0, 0, 0);
+        // (or, when a launch continues an earlier frame range, the state that launch left: the bf16 B-operand tiles)
+        int4 *carry = P.state ? reinterpret_cast<int4 *>(P.state) + (size_t)tile * ((S::kX1Bytes + S::kH2Bytes) / 16) : nullptr;
+        if (carry && P.f0 > 0) {
+            for (int i = tid; i < S::kX1Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(x1[0])[i] = carry[i];
+            for (int i = tid; i < S::kH2Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(h2t)[i] = carry[S::kX1Bytes / 16 + i];
+        } else {
+            for (int i = tid; i < S::kX1Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(x1[0])[i] = make_int4(0, 0, 0, 0);
+            for (int i = tid; i < S::kH2Bytes / 16; i += kComputeThreads) reinterpret_cast<int4 *>(h2t)[i] = make_int4(0, 0, 0, 0);
+        }
         for (int i = tid; i < NU * kLdR; i += kComputeThreads) rs[i] = 0.0f;
         umma::fence_async_smem();
         named_bar_sync(1, kComputeThreads);
         if (lane == 0) mbar_arrive(act_ready);
 
-        for (int fr = 0; fr < P.L; ++fr) {
+        for (int fr = P.f0; fr < P.f1; ++fr) {
             float featv[NE], fov[NE], rsv[NE];
 #pragma unroll
             for (int e2 = 0; e2 < NE; ++e2) {
@@ -528,10 +535,15 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             }
             umma::fence_async_smem();
             named_bar_sync(1, kComputeThreads);
-            if (lane == 0 && fr + 1 < P.L) mbar_arrive(act_ready);
+            if (lane == 0 && fr + 1 < P.f1) mbar_arrive(act_ready);
             FPC_PHASE(kPhOut);
             if (prof) pt[kPhFrames] += 1;
             cur ^= 1;
+        }
+        if (carry) {       // x1[cur] = [next input frame | h1], h2t = h2: everything the next frame range needs
+            for (int i = tid; i < S::kX1Bytes / 16; i += kComputeThreads) carry[i] = reinterpret_cast<const int4 *>(x1[cur])[i];
+            for (int i = tid; i < S::kH2Bytes / 16; i += kComputeThreads) carry[S::kX1Bytes / 16 + i] = reinterpret_cast<const int4 *>(h2t)[i];
+            named_bar_sync(1, kComputeThreads);
         }
     }
     if (prof)
@@ -555,8 +567,16 @@ static int launch_encode_bf16(const EncodeParams &P, int grid, cudaStream_t st)
     return FPC_OK;
 }
 
+size_t encode_bf16_state_bytes(int B)
+{
+    if (B <= 0) return 0;
+    // per utterance: the [x(32) | h1(384)] and h2(128) bf16 rows; tiles are padded to at most 64 utterances
+    return (size_t)(B + 64) * (size_t)(kXK + kH2) * 2;
+}
+
 int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu)
 {
+    if (P.f0 < 0 || P.f1 > P.L || P.f0 >= P.f1) return FPC_ERR_ARG;
     const int sms = num_sms();
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
     int nu = force_nu;

@@ -238,7 +238,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         const int b0 = tile * MT;
         float *cur = setA, *nxt = setB;
-        float *carry = P.state ? P.state + (size_t)tile * (S::kStateSet + MT * kLdX) : nullptr;
+        float *carry = P.state ? reinterpret_cast<float *>(P.state) + (size_t)tile * (S::kStateSet + MT * kLdX) : nullptr;
         if (carry && P.f0 > 0) {       // continue the recurrence where the launch of the previous frame range stopped
             for (int i = tid; i < S::kStateSet; i += kComputeThreads) cur[i] = carry[i];
             for (int i = tid; i < MT * kLdX; i += kComputeThreads) xin[i] = carry[S::kStateSet + i];

@@ -181,8 +181,7 @@ typedef struct fpc_encode_host_io {
 /* device scratch fpc_encode_host needs: the device copies of the input, of every output, and the carried state */
 size_t fpc_encode_host_workspace_bytes(int B, int L, int precision);
 
-/* chunks <= 0: chosen by the library (48+ frames per range, at most 16 ranges).  FPC_PREC_BF16 runs as one
- * range (its kernel does not carry state between launches yet). */
+/* chunks <= 0: chosen by the library (48+ frames per range, at most 16 ranges). */
 int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_host_io *io,
                     int precision, int chunks, void *d_workspace, size_t workspace_bytes, void *stream);
 

@@ -121,3 +121,17 @@ def test_bf16_vs_fp32_oracle_tolerance(torch_cuda, model16, synth, cfgdir, oracl
     err = np.abs(g["r"] - o["r"]).max()
     print("bf16 residual mode (all frames above threshold => teacher forced): max abs residual diff %.3g" % err)
     assert err <= PRED_TOL
+
+
+@pytest.mark.parametrize("B,L,chunks", [(70, 40, 3), (200, 24, 0), (5, 9, 4)])
+def test_bf16_encode_host_matches_device_path(torch_cuda, model16, synth, cfgdir, B, L, chunks):
+    """The host-buffer call cuts the utterances along time and carries the bf16 recurrent state (the B-operand tiles)
+    between launches: every output equals the single-launch device call bit for bit."""
+    torch = torch_cuda
+    cfg, _ = cfgdir
+    feat = synth.make_features(B, L, first_utt=8200)
+    ref = encode(torch, model16, cfg, feat, 0.25, 2.1)
+    host = model16.encode_host(cfg, torch.from_numpy(feat).pin_memory(), 0.25, 2.1, chunks=chunks)
+    torch.cuda.synchronize()
+    for k in ("c_in", "r", "r_qtz", "ind1", "ind2", "idx"):
+        assert np.array_equal(host[k].numpy(), ref[k]), "bf16 encode_host differs in %s" % k

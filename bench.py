@@ -139,10 +139,14 @@ def cpu_encode_rate(S, n_frames, l1, l2, target_seconds, first_utt=0):
     w = O.weights_from_state_dict(sd)
     cbs = S.make_codebooks(0)
     C = O.Codebooks(cbs["cb_path"], cbs["scl_cb_path"], cbs["bl_cb_path"], cbs["bl_scl_cb_path"])
-    threads = O.num_threads()
+    # every host thread this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for its children
+    try:
+        threads = len(os.sched_getaffinity(0))
+    except AttributeError:
+        threads = os.cpu_count() or 1
     probe = S.make_features(threads, min(n_frames, 50), first_utt=first_utt)
     t0 = time.perf_counter()
-    O.encode(w, C, probe, l1, l2)
+    O.encode(w, C, probe, l1, l2, nthreads=threads)
     rate = probe.shape[0] * probe.shape[1] / max(time.perf_counter() - t0, 1e-6)
     n_utts = max(threads, int(rate * target_seconds / n_frames) // threads * threads)
     feat = S.make_features(min(n_utts, 64), n_frames, first_utt=first_utt)
@@ -151,7 +155,7 @@ def cpu_encode_rate(S, n_frames, l1, l2, target_seconds, first_utt=0):
 
     def step():
         t = time.perf_counter()
-        O.encode(w, C, feat, l1, l2)
+        O.encode(w, C, feat, l1, l2, nthreads=threads)
         return time.perf_counter() - t
     return step, n_utts, threads
 

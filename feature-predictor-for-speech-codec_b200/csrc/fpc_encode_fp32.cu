@@ -8,18 +8,19 @@
 // decoded frame that is fed back and all quantiser scratch live in shared memory.
 //
 // Work split inside a CTA (384 threads = 3 warpgroups; setmaxnreg moves the producer group's
-// registers to the two compute groups):
+// registers to the two compute groups, 232 / 40 per thread):
 //   warps 0..7  compute.  Thread (tg = warp>>1, ug = (warp&1)*32 + lane) owns hidden units
 //               {2ug, 2ug+1} (+128*pass) for utterances {tg, tg+4, ..., tg+4(TU-1)} of the tile,
 //               i.e. a TU x 2 x {r,z,n_i,n_h} register tile; every dot product is one
 //               ascending-k FFMA chain (the canonical order the oracle follows).
-//   warp 8      producer (warps 9..11 only exist to complete the warpgroup).  One lane streams the 2.65 MB packed weight image through an
-//               8-stage shared-memory ring with 1-D bulk async copies (TMA engine, UBLKCP),
-//               mbarrier full/empty handshakes; the image stays L2-resident (it is re-read by
-//               every CTA every frame) and the ring runs ahead across frame boundaries.
-// After the GRUs: FC + 2*tanh, residual, thresholds, scalar quantiser (one warp per
-// utterance), then the m-best VQ search with each thread holding 4 codewords of each stage in
-// registers and the tile's residual vectors broadcast from shared memory.
+//   warp 8      producer (warps 9..11 only exist to complete the warpgroup).  One lane streams the 2.68 MB packed
+//               weight image (217 groups of 12 KB per frame) through a 4-stage shared-memory ring with 1-D bulk
+//               async copies (TMA engine, UBLKCP), mbarrier full/empty handshakes; the image stays L2-resident (it is
+//               re-read by every CTA every frame) and the ring runs ahead across frame boundaries.
+// After the GRUs: FC + 2*tanh, residual, thresholds, scalar quantiser (one warp per utterance), then the screened
+// m-best VQ search (fpc_vq_screen.cuh) with the tile's residual vectors broadcast from shared memory.
+// A launch covers the frame range [f0, f1) of every utterance; with EncodeParams::state the recurrent state of each
+// tile is carried from one launch to the next (fpc_encode_host cuts a batch along time that way).
 #include "fpc_common.cuh"
 #include "fpc_math.cuh"
 #include "fpc_vq.cuh"
@@ -66,7 +67,7 @@ struct Pipe {
 };
 
 // ------------------------------------------------------------------------------------------
-// one "part" of a pass: NG groups of 4 k, accumulating into r, z and the third gate (n_i or n_h)
+// one "part" of a pass: NG groups of 8 k, accumulating into r, z and the third gate (n_i or n_h)
 // (Measured and rejected on the B200: weight tile of group g+1 prefetched into a second register buffer, barrier
 // probed two groups ahead, whole 4-k chunks prefetched with the rows innermost, two groups per barrier round trip,
 // two half-size CTAs per SM -- all equal or slower than this plain loop; ptxas orders loads and FMAs by operand

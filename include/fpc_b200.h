@@ -9,6 +9,8 @@
  *   fpc_encode                 <- models/wavernn.py:165-256   Wavernn.encoder (whole frame loop,
  *                                 including the injected vq_quantize / scl_quantize calls at
  *                                 :219-240 and the feedback at :242,252)
+ *   fpc_encode_host            <- synthesis_qtz.py:149-160, generate_qtz_features.py:55-70   the host sequence
+ *                                 feat.to('cuda') -> encoder -> results .cpu(), copies overlapped with the kernel
  *   fpc_decode                 <- models/wavernn.py:367-379   Wavernn.decoder (receiver replay)
  *   fpc_pack_weights           <- models/wavernn.py:37-38,48-52  parameters of rnn1/rnn2/dual_fc
  *   fpc_pack_codebooks         <- quantization/vq_func.py:141,171  the np.load of the four files

@@ -169,3 +169,47 @@ def test_kmeans_reduce_world_size_2_gloo(tmp_path):
         outs.append(o)
     for r, (p, o) in enumerate(zip(procs, outs)):
         assert p.returncode == 0 and "ok" in o, "rank %d failed:\n%s" % (r, o)
+
+
+def test_lpcnet_chunks_is_the_reference_strided_view():
+    """fpc_features.lpcnet_chunks against the as_strided of generate_qtz_features.py:66-70 (pure tensor logic, CPU)."""
+    import torch
+    import fpc_features
+    L = 200
+    a = np.arange(L * 36, dtype=np.float32).reshape(1, L, 36)
+    s = a.strides[-1]
+    want = np.lib.stride_tricks.as_strided(a.flatten(), shape=(10, 19, 36), strides=(15 * 36 * s, 36 * s, s))
+    got = fpc_features.lpcnet_chunks(torch.from_numpy(a)[0], n_chunks=10)
+    assert np.array_equal(got.numpy(), want)
+    every = fpc_features.lpcnet_chunks(torch.from_numpy(a))
+    assert tuple(every.shape) == (1, (L - 19) // 15 + 1, 19, 36)
+    assert np.array_equal(every[0, -1].numpy(), a[0, 15 * (every.shape[1] - 1):15 * (every.shape[1] - 1) + 19])
+    with pytest.raises(ValueError):
+        fpc_features.lpcnet_chunks(torch.from_numpy(a)[0, :150], n_chunks=10)     # the reference would read past the end
+    assert tuple(fpc_features.lpcnet_chunks(torch.from_numpy(a)[0, :10]).shape) == (0, 19, 36)
+
+
+def test_frame_word_layout_is_documented_and_disjoint():
+    import fpc_bitstream
+    bits = np.zeros(32, dtype=int)
+    for name, (lo, n) in fpc_bitstream.WORD_BITS.items():
+        bits[lo:lo + n] += 1
+    assert bits.max() == 1 and bits[:30].min() == 1 and bits[30:].sum() == 0     # 30 payload bits, no overlap
+    hdr = open(os.path.join(ROOT, "include", "fpc_b200.h")).read()
+    assert "bits 2-9 scalar index" in hdr and "bits 20-29 VQ stage-2 index" in hdr
+
+
+def test_no_cpu_fallback_in_new_host_modules():
+    """CPU tensors are an error, not a slow path (no GPU needed to check that)."""
+    import torch
+    import fpc_native
+    import fpc_train
+    import fpc_features
+    if torch.cuda.is_available():
+        pytest.skip("checks the behaviour without a GPU")
+    with pytest.raises(fpc_native.FpcError):
+        fpc_train.compact_rows(torch.zeros(4, 18), 1, 17)
+    with pytest.raises(fpc_native.FpcError):
+        fpc_features.lpcnet_features(torch.zeros(1, 4, 20))
+    with pytest.raises(fpc_native.FpcError):
+        fpc_train.scalar_codebook(torch.zeros(10), 4)

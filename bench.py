@@ -428,6 +428,21 @@ def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
         dt = time.perf_counter() - t0
         res["e2e_host_call"] = {"call": "cb_func.update(host array, K=512)", "vectors": nh, "seconds": dt,
                                 "h2d_bytes": nh * 68, "iters_per_s_scaled_to_all_vectors": nh / dt / n_total}
+        # the whole grow-by-one LBG schedule of cb_func.vq_train (cb_func.py:28-54): 4 (K - 1) + 10 Lloyd iterations with K
+        # growing from 1 to 1024, on a bounded sample so the default run stays short
+        nv = min(n_total, args.vq_train_vectors)
+        if nv > 0:
+            sub = data[:nv].contiguous()
+            torch.cuda.synchronize()
+            n0 = fpc_native.launch_count()
+            t0 = time.perf_counter()
+            cb_func.vq_train(sub, np.zeros((1024, 17)), 1024, rng=np.random.RandomState(0))
+            torch.cuda.synchronize()
+            dt = time.perf_counter() - t0
+            res["vq_train"] = {"call": "cb_func.vq_train(data, codebook, 1024)", "vectors": nv, "updates": 4 * 1023 + 10,
+                               "seconds": dt, "gpu_launches": int(fpc_native.launch_count() - n0),
+                               "note": "wall clock incl. the host loop; the reference runs the same schedule with "
+                                       "cb_func.update at 0.39 iters/s for N=20000, K=1024 (BASELINE.md)"}
         sys.path.insert(0, os.path.join(ROOT, "oracle"))
         import oracle as O
         ns = 200_000
@@ -531,6 +546,7 @@ def main():
     ap.add_argument("--bf16-steps", type=int, default=3)
     ap.add_argument("--kmeans-vectors", type=int, default=50_000_000, help="total residual vectors (all ranks)")
     ap.add_argument("--kmeans-iters", type=int, default=3)
+    ap.add_argument("--vq-train-vectors", type=int, default=2_000_000, help="sample for the full vq_train schedule (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-chunks", type=int, default=0, help="frame ranges of the host-buffer call (0 = library default)")
     args = ap.parse_args()

@@ -68,7 +68,7 @@ __device__ __forceinline__ double exact17(const float (&x)[kDim], const double *
 // one vector per thread; codebook (float64 + fp32 shadow) resident in shared memory
 __global__ void __launch_bounds__(kKmThreads, 1)
 kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__restrict__ cb, int K,
-                     double *__restrict__ sums, double *__restrict__ counts, int32_t *__restrict__ idx_out)
+                     double *__restrict__ sums, double *__restrict__ counts, int32_t *__restrict__ idx_out, int R)
 {
     extern __shared__ __align__(16) unsigned char smem[];
     double *cb64 = reinterpret_cast<double *>(smem);                              // [K][18]
@@ -222,7 +222,20 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
             // (uniform full-mask shuffles, ascending lane order).
             if (sums) {
                 const int key = valid ? b : -1;
-                if (K <= 32) {
+                if (R > 1) {
+                    // Small codebooks (the grow-by-one schedule of vq_train spends most of its 4102 iterations there,
+                    // cb_func.py:34-47) would hammer a handful of addresses: the table is replicated R times in the
+                    // workspace (R K >= 512 rows), every thread adds into its own replica -- lanes of a warp never
+                    // collide while R >= 32 -- and kmeans_fold_kernel sums the replicas in a fixed order.
+                    if (valid) {
+                        const int rep = (int)(((long)blockIdx.x * kKmThreads + threadIdx.x + (long)j * 7) % R);
+                        double *s2 = sums + ((size_t)rep * K + b) * kDim;
+#pragma unroll
+                        for (int d = 0; d < kDim; ++d) atomicAdd(s2 + d, (double)x[d]);
+                        atomicAdd(counts + (size_t)rep * K + b, 1.0);
+                    }
+                } else if (K <= 32) {
+                    // no workspace: lanes that chose the same centroid are merged first (uniform full-mask shuffles)
                     const unsigned peers = __match_any_sync(0xffffffffu, key);
                     const int leader = __ffs(peers) - 1;
                     double acc[kDim];
@@ -248,6 +261,23 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                 }
             }
         }
+    }
+}
+
+// sums[k][d] += sum_r ws_sums[r][k][d], counts[k] += sum_r ws_counts[r][k]  (ascending r: a fixed order)
+__global__ void kmeans_fold_kernel(const double *__restrict__ ws_sums, const double *__restrict__ ws_counts, int R, int K,
+                                   double *__restrict__ sums, double *__restrict__ counts)
+{
+    const int t = blockIdx.x * blockDim.x + threadIdx.x;
+    if (t < K * kDim) {
+        double a = 0.0;
+        for (int r = 0; r < R; ++r) a += ws_sums[(size_t)r * K * kDim + t];
+        sums[t] += a;
+    } else if (t < K * kDim + K) {
+        const int k = t - K * kDim;
+        double a = 0.0;
+        for (int r = 0; r < R; ++r) a += ws_counts[(size_t)r * K + k];
+        counts[k] += a;
     }
 }
 
@@ -312,17 +342,21 @@ using namespace fpc;
 
 extern "C" {
 
+// replicas of the (K,17)+(K) accumulation table: R K >= 512 rows, none from 512 entries up
+static int kmeans_replicas(int K) { return K >= 512 ? 1 : (512 + K - 1) / K; }
+
 size_t fpc_kmeans_workspace_bytes(long N, int K)
 {
-    (void)N; (void)K;
-    return 0;
+    (void)N;
+    if (K < 1) return 0;
+    const int R = kmeans_replicas(K);
+    return R > 1 ? (size_t)R * K * (kDim + 1) * sizeof(double) : 0;
 }
 
 int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
                                  double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
                                  void *stream)
 {
-    (void)d_workspace; (void)workspace_bytes;
     if (N < 0 || K < 1) return FPC_ERR_ARG;
     if (K > FPC_MAX_VQ_ENTRIES) return FPC_ERR_CODEBOOK;
     if (N == 0) return FPC_OK;
@@ -341,7 +375,18 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     }
     long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;
-    kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, d_sums, d_counts, d_idx);
+    // with a workspace and a small codebook the sums go to replicated tables first (see the kernel)
+    int R = d_sums ? kmeans_replicas(K) : 1;
+    if (R > 1 && (!d_workspace || workspace_bytes < fpc_kmeans_workspace_bytes(N, K))) R = 1;
+    double *acc_sums = d_sums, *acc_counts = d_counts;
+    if (R > 1) {
+        acc_sums = (double *)d_workspace;
+        acc_counts = acc_sums + (size_t)R * K * kDim;
+        FPC_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, (size_t)R * K * (kDim + 1) * sizeof(double), st));
+    }
+    kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
+    FPC_LAUNCH_CHECK();
+    if (R > 1) kmeans_fold_kernel<<<(K * (kDim + 1) + 255) / 256, 256, 0, st>>>(acc_sums, acc_counts, R, K, d_sums, d_counts);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

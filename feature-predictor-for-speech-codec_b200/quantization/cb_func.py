@@ -61,10 +61,14 @@ def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
     counts = torch.zeros((K,), dtype=torch.float64, device=dev) if want_sums else None
     idx = torch.empty((n,), dtype=torch.int32, device=dev) if want_idx else None
     with torch.cuda.device(dev):
+        # scratch for the replicated accumulation tables of small codebooks (0 bytes from 512 entries up)
+        need = N.lib().fpc_kmeans_workspace_bytes(n, K) if want_sums else 0
+        ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
         N.check(N.lib().fpc_kmeans_assign_accumulate(
             data_dev.data_ptr(), n, cb_dev.data_ptr(), K,
             sums.data_ptr() if want_sums else None, counts.data_ptr() if want_sums else None,
-            idx.data_ptr() if want_idx else None, None, 0, N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
+            idx.data_ptr() if want_idx else None, ws.data_ptr() if ws is not None else None, need,
+            N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
     return sums, counts, idx
 
 
@@ -124,9 +128,12 @@ def quantize(codebook, data):
 
 
 def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
-    """cb_func.py:28-54.  The residuals go to the device once; each of the 4(K-1)+10 Lloyd
-    iterations is one assign kernel, one (optional) all-reduce and one finalize kernel, with the
-    codebook staying on the device between iterations of a growth step."""
+    """cb_func.py:28-54.  The residuals go to the device once and the codebook stays there for the whole schedule:
+    each of the 4(K-1)+10 Lloyd iterations is one assign kernel, one (optional) all-reduce and one finalize kernel,
+    and the grow-by-one step (copy entry 0, add the jitter) is two small device operations, so the host never waits
+    for the GPU inside the loop.  The jitter is the reference's: `.001 * np.random.rand(e, ndims) / 2` drawn for
+    e = 1, 2, ... from NumPy's global RNG (:41) -- drawn here in one call, which yields the same numbers because
+    consecutive `rand` calls continue one stream."""
     torch = _torch()
     d = _data_on_device(data)
     dev = d.device
@@ -136,21 +143,26 @@ def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
     # codebook[0] = np.mean(data, 0)  (:33): float64 mean of the (global) data
     col_sum = d.to(torch.float64).sum(0)
     n_total = fpc_dist.allreduce_kmeans(col_sum, None, d.shape[0], group)
-    codebook[0] = (col_sum / float(n_total)).cpu().numpy()
-    e = 1
+    cb_full = torch.from_numpy(np.ascontiguousarray(codebook[:nb_entries])).to(dev)
+    cb_full[0] = col_sum / float(n_total)
+    n_draws = ndims * (nb_entries - 1) * nb_entries // 2
+    jitter = None
+    if n_draws > 0:
+        flat = fpc_dist.broadcast_array(.001 * (draw(n_draws) / 2), group)      # rank 0's draw when distributed
+        jitter = torch.from_numpy(np.ascontiguousarray(flat)).to(dev)
+    e, off = 1, 0
     while e < nb_entries:
-        codebook[e, :] = codebook[0, :]
-        delta = fpc_dist.broadcast_array(.001 * (draw(e, ndims) / 2), group)
-        codebook[:e, :] += delta
+        cb_full[e] = cb_full[0]
+        cb_full[:e] += jitter[off:off + e * ndims].view(e, ndims)
+        off += e * ndims
         e += 1
-        cb = torch.from_numpy(np.ascontiguousarray(codebook[:e])).to(dev)
         for _ in range(4):
-            cb, stats, _ = update_device(d, cb, group)
-        codebook[:e, :] = cb.cpu().numpy()
+            cb, stats, _ = update_device(d, cb_full[:e], group)
+            cb_full[:e] = cb
         if verbose and fpc_dist.rank(group) == 0:
             s = stats.cpu().numpy()
             print('{} - min: {}, max: {}, small: {}, error: {}'.format(e, s[0], s[1], int(s[2]), s[3]))
-    cb = torch.from_numpy(np.ascontiguousarray(codebook[:nb_entries])).to(dev)
+    cb = cb_full[:nb_entries]
     for _ in range(10):
         cb, stats, _ = update_device(d, cb, group)
     return cb.cpu().numpy()

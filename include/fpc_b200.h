@@ -223,7 +223,9 @@ int fpc_scl_quantize(const float *d_x, long n, const void *d_codes, int dtype, i
 /* One assignment pass of cb_func.update over this rank's shard: nearest centroid in float64
  * direct form (first minimum), then per-centroid float64 sums and counts ADDED into d_sums (K,17)
  * and d_counts (K) (caller zeroes them; with several ranks the caller all-reduces them before
- * fpc_kmeans_finalize).  d_idx (N) int32 may be NULL.  d_workspace: fpc_kmeans_workspace_bytes. */
+ * fpc_kmeans_finalize).  d_idx (N) int32 may be NULL.  d_workspace: fpc_kmeans_workspace_bytes(N, K) bytes of
+ * scratch for codebooks below 512 entries (replicated accumulation tables that keep the float64 atomics of small
+ * codebooks off a handful of addresses); NULL is allowed and only slower. */
 size_t fpc_kmeans_workspace_bytes(long N, int K);
 int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
                                  double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,

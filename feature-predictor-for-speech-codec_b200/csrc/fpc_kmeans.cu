@@ -286,6 +286,23 @@ __global__ void kmeans_finalize_kernel(const double *__restrict__ sums, const do
                                        double n_total, double *__restrict__ cb_out, double *__restrict__ stats)
 {
     __shared__ double s_min[32], s_max[32], s_empty[32], s_w2[32];
+    __shared__ double s_n;
+    if (!(n_total > 0.0)) {
+        // nb_vectors = sum of the counts (exact: they are integers), so callers need not bring it from the host
+        double c = 0.0;
+        for (int k = threadIdx.x; k < K; k += blockDim.x) c += counts[k];
+        for (int off = 16; off > 0; off >>= 1) c += __shfl_xor_sync(0xffffffffu, c, off);
+        if ((threadIdx.x & 31) == 0) s_min[threadIdx.x >> 5] = c;
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double t = 0.0;
+            for (int w = 0; w < (int)(blockDim.x >> 5); ++w) t += s_min[w];
+            s_n = t;
+        }
+        __syncthreads();
+        n_total = s_n;
+        __syncthreads();
+    }
     double mn = 1e300, mx = -1e300, em = 0.0, w2 = 0.0;
     for (int k = threadIdx.x; k < K; k += blockDim.x) {
         const double c = counts[k];
@@ -318,7 +335,7 @@ __global__ void kmeans_finalize_kernel(const double *__restrict__ sums, const do
             em += __shfl_xor_sync(0xffffffffu, em, off);
             w2 += __shfl_xor_sync(0xffffffffu, w2, off);
         }
-        if (lane == 0 && stats) { stats[0] = mn; stats[1] = mx; stats[2] = em; stats[3] = w2; }
+        if (lane == 0 && stats) { stats[0] = mn; stats[1] = mx; stats[2] = em; stats[3] = w2; stats[4] = n_total; }
     }
 }
 

@@ -43,14 +43,15 @@ def shard_range(n_units, rank_, world):
     return first, base + (1 if rank_ < extra else 0)
 
 
-def allreduce_kmeans(sums, counts, n_local, group=None):
+def allreduce_kmeans(sums, counts, n_local, group=None, want_total=True):
     """In-place SUM of the per-centroid accumulators over all ranks; returns the global number
-    of vectors (cb_func.py:94 divides the counts by it).  `counts` may be None."""
+    of vectors (cb_func.py:94 divides the counts by it).  `counts` may be None.
+    want_total=False skips the device->host read of that number (returns None): the Lloyd loop
+    does not need it on the host, fpc_kmeans_finalize derives it from the counts."""
     if not is_distributed(group):
         return int(n_local)
     import torch
     dist = _dist()
-    k = sums.shape[0]
     flat = torch.empty(sums.numel() + (counts.numel() if counts is not None else 0) + 1, dtype=torch.float64,
                        device=sums.device)
     flat[:sums.numel()] = sums.reshape(-1)
@@ -61,7 +62,8 @@ def allreduce_kmeans(sums, counts, n_local, group=None):
     sums.copy_(flat[:sums.numel()].reshape(sums.shape))
     if counts is not None:
         counts.copy_(flat[sums.numel():-1].reshape(counts.shape))
-    del k
+    if not want_total:
+        return None
     return int(round(float(flat[-1].item())))
 
 

@@ -73,20 +73,21 @@ def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
 
 
 def update_device(data_dev, cb_dev, group=None):
-    """One Lloyd iteration entirely on the device (+ the all-reduce when distributed).
-    Returns (new codebook (K,17) f64 device tensor, stats (4,) f64 device tensor,
-    global vector count)."""
+    """One Lloyd iteration entirely on the device (+ the all-reduce when distributed), no host synchronisation.
+    Returns (new codebook (K,17) f64 device tensor, stats (5,) f64 device tensor = min count, max count, #empty,
+    sum (count/N)^2, N; the global vector count N as a 0-d device tensor view of stats[4])."""
     torch = _torch()
     dev = data_dev.device
     K = cb_dev.shape[0]
     sums, counts, _ = assign_accumulate(data_dev, cb_dev)
-    n_total = fpc_dist.allreduce_kmeans(sums, counts, data_dev.shape[0], group)
+    fpc_dist.allreduce_kmeans(sums, counts, data_dev.shape[0], group, want_total=False)
     out = torch.empty((K, 17), dtype=torch.float64, device=dev)
-    stats = torch.empty((4,), dtype=torch.float64, device=dev)
+    stats = torch.empty((5,), dtype=torch.float64, device=dev)
     with torch.cuda.device(dev):
-        N.check(N.lib().fpc_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), K, float(n_total), out.data_ptr(),
+        # n_total = 0: nb_vectors is the sum of the (all-reduced) counts, taken on the device
+        N.check(N.lib().fpc_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), K, 0.0, out.data_ptr(),
                                             stats.data_ptr(), N.current_stream(dev)), "fpc_kmeans_finalize")
-    return out, stats, n_total
+    return out, stats, stats[4]
 
 
 def find_nearest(data, codebook):

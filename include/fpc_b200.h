@@ -230,7 +230,9 @@ size_t fpc_kmeans_workspace_bytes(long N, int K);
 int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
                                  double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
                                  void *stream);
-/* codebook = sums / (counts + 1e-20); stats[4] = {min count, max count, #empty, sum (count/N)^2} */
+/* codebook = sums / (counts + 1e-20); stats[5] = {min count, max count, #empty, sum (count/N)^2, N}.
+ * n_total <= 0: N is taken as the sum of the counts (what nb_vectors is), which saves a host round trip per
+ * iteration when the counts were all-reduced on the device. */
 int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, double n_total, double *d_cb_out,
                         double *d_stats, void *stream);
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */

@@ -70,7 +70,9 @@ struct Pipe {
 // one "part" of a pass: NG groups of 8 k, accumulating into r, z and the third gate (n_i or n_h)
 // (Measured and rejected on the B200: weight tile of group g+1 prefetched into a second register buffer, barrier
 // probed two groups ahead, whole 4-k chunks prefetched with the rows innermost, two groups per barrier round trip,
-// two half-size CTAs per SM -- all equal or slower than this plain loop; ptxas orders loads and FMAs by operand
+// two half-size CTAs per SM, all operands of group g+1 loaded at the end of iteration g (26 LDS, then 168 FFMA2 with
+// nothing in between: 275 k cycles instead of 223 k, also with the two warps of a scheduler skewed by half a group)
+// -- all equal or slower than this plain loop; ptxas orders loads and FMAs by operand
 // readiness whatever the source says.  tools/gemm_bounds.sh: the weight stream alone needs 51 k cycles per frame,
 // the arithmetic alone 214 k of the 223 k the stage takes.)
 // ------------------------------------------------------------------------------------------

@@ -35,7 +35,7 @@ constexpr int kThreads = kComputeThreads + 128;   // 2 compute warpgroups + 1 pr
 constexpr int kLd1 = kH1 + 4;          // 388: padded row strides (floats) -> conflict-free float4 rows
 constexpr int kLd2 = kH2 + 4;          // 132
 constexpr int kLdX = 24;               // input frame row (20 used)
-constexpr int kLdFc = kH2 + 1;         // 129
+constexpr int kLdFc = kH2 + 4;         // 132: float4-aligned rows, conflict-free for 8 consecutive rows
 
 template <int TU> struct Smem {
     static constexpr int MT = 4 * TU;
@@ -285,21 +285,44 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
 
             FPC_PHASE(kPhGru);
             // ---- relu, dual_fc, 2*tanh (wavernn.py:87-92); residual (:196) ----
+            {
+                // the thread's NE outputs advance together (NE independent ascending-k chains, operands as float4)
+                float acc[NE];
+                const float4 *wr4[NE], *hv4[NE];
+                bool on[NE];
 #pragma unroll
-            for (int q = 0; q < NE; ++q) {
-                const int e = tid + kComputeThreads * q;
-                const int u = e / 20, j = e - u * 20;
-                if (e < MT * 20 && j < kFc) {
-                    float a = bfc[j];
-                    const float *wr = wfc + j * kLdFc;
-                    const float *hv = h2n + u * kLd2;
-#pragma unroll 8
-                    for (int k = 0; k < kH2; ++k) a = __fmaf_rn(wr[k], fmaxf(hv[k], 0.0f), a);
-                    const float f = __fmul_rn(2.0f, tanh_c(a));
-                    fov[q] = f;
-                    if (P.mode != kModeDecode) {
-                        rsv[q] = __fsub_rn(featv[q], f);
-                        rs[u * kLdR + 3 + j] = rsv[q];
+                for (int q = 0; q < NE; ++q) {
+                    const int e = tid + kComputeThreads * q;
+                    const int u = e / 20, j = e - u * 20;
+                    on[q] = e < MT * 20 && j < kFc;
+                    acc[q] = on[q] ? bfc[j] : 0.0f;
+                    wr4[q] = reinterpret_cast<const float4 *>(wfc + (on[q] ? j : 0) * kLdFc);
+                    hv4[q] = reinterpret_cast<const float4 *>(h2n + (on[q] ? u : 0) * kLd2);
+                }
+#pragma unroll 4
+                for (int k4 = 0; k4 < kH2 / 4; ++k4) {
+#pragma unroll
+                    for (int q = 0; q < NE; ++q) {
+                        const float4 w4 = wr4[q][k4], h4 = hv4[q][k4];
+                        float a = acc[q];
+                        a = __fmaf_rn(w4.x, fmaxf(h4.x, 0.0f), a);
+                        a = __fmaf_rn(w4.y, fmaxf(h4.y, 0.0f), a);
+                        a = __fmaf_rn(w4.z, fmaxf(h4.z, 0.0f), a);
+                        a = __fmaf_rn(w4.w, fmaxf(h4.w, 0.0f), a);
+                        acc[q] = a;
+                    }
+                }
+#pragma unroll
+                for (int q = 0; q < NE; ++q) {
+                    if (on[q]) {
+                        const int e = tid + kComputeThreads * q;
+                        const int u = e / 20, j = e - u * 20;
+                        const float f = __fmul_rn(2.0f, tanh_c(acc[q]));
+                        fov[q] = f;
+                        if (P.mode != kModeDecode) {
+                            rsv[q] = __fsub_rn(featv[q], f);
+                            rs[u * kLdR + 3 + j] = rsv[q];
+                        }
                     }
                 }
             }

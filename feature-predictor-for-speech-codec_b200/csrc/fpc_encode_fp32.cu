@@ -50,7 +50,8 @@ template <int TU> struct Smem {
     static constexpr int offRq = offRs + MT * kLdR * 4;                  // quantised residual rows (stride 20)
     static constexpr int offMisc = offRq + MT * 20 * 4;
     // misc: m1[MT] m2[MT] (float), idx0/idx1/idx2[MT] (int), listA[MT] listB[MT] (int), counts[4]
-    static constexpr int offBars = offMisc + (7 * MT + 4) * 4;
+    static constexpr int offScl = ((offMisc + (7 * MT + 4) * 4 + 15) / 16) * 16;   // both scalar tables, file dtype, 2 x 2 KB
+    static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8;
     static constexpr int total = ((offBars + 2 * kStages * 8 + 127) / 128) * 128;
     // VQ scratch aliases the DEAD state set (the one holding the previous frame's h1/h2)
     static constexpr int kScratchBytes = kStateSet * 4;
@@ -178,6 +179,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     int *listA = idx2s + MT;
     int *listB = listA + MT;
     int *counts = listB + MT;
+    unsigned char *sclbuf = smem + S::offScl;
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::offBars);
     uint64_t *empty = full + kStages;
 
@@ -232,6 +234,16 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
         for (int i = tid; i < kBiasFloats; i += kComputeThreads) bias[i] = tail[i];
         for (int i = tid; i < kFcFloats; i += kComputeThreads) wfc[(i >> 7) * kLdFc + (i & 127)] = tail[kBiasFloats + i];
         if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
+        // the scalar tables (<= 256 levels each) next to the state: the VQ streams 150 KB of codebook through L1 every
+        // frame, so from global memory every scalar search paid L2 latencies
+        if (cbh != nullptr) {
+            const long long *src0 = reinterpret_cast<const long long *>(P.cb + cbh->scl.off);
+            const long long *src1 = reinterpret_cast<const long long *>(P.cb + cbh->blscl.off);
+            const int n0 = cbh->scl.n * (cbh->scl.dtype == FPC_F32 ? 4 : 8), n1 = cbh->blscl.n * (cbh->blscl.dtype == FPC_F32 ? 4 : 8);
+            for (int i = tid; i < (n0 + 7) / 8; i += kComputeThreads) reinterpret_cast<long long *>(sclbuf)[i] = src0[i];
+            for (int i = tid; i < (n1 + 7) / 8; i += kComputeThreads)
+                reinterpret_cast<long long *>(sclbuf + FPC_MAX_SCL_ENTRIES * 8)[i] = src1[i];
+        }
     }
     Pipe pp{0, 0u};
     const bool prof = P.prof != nullptr && tid == 0;
@@ -353,16 +365,17 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                     int i0 = -1;
                     if (P.mode == kModeQuantize && valid) {
                         const PackedScl &sb = (m1 != 0.0f) ? cbh->scl : cbh->blscl;
+                        const unsigned char *sclt = sclbuf + ((m1 != 0.0f) ? 0 : FPC_MAX_SCL_ENTRIES * 8);
                         if (sb.n > 0) {
                             const float x0 = rs[u * kLdR + 3];
                             float qv;
                             if (sb.dtype == FPC_F32) {
                                 float q;
-                                i0 = warp_scl_nearest<float>(reinterpret_cast<const float *>(P.cb + sb.off), sb.n, x0, lane, q);
+                                i0 = warp_scl_nearest<float>(reinterpret_cast<const float *>(sclt), sb.n, x0, lane, q);
                                 qv = q;
                             } else {
                                 double q;
-                                i0 = warp_scl_nearest<double>(reinterpret_cast<const double *>(P.cb + sb.off), sb.n, x0, lane, q);
+                                i0 = warp_scl_nearest<double>(reinterpret_cast<const double *>(sclt), sb.n, x0, lane, q);
                                 qv = (float)q;
                             }
                             if (lane == 0) rq[u * 20] = qv;

@@ -71,17 +71,24 @@ __device__ __forceinline__ void warp_argmin(float &d, int &i, int /*tag*/)
 }
 
 // scalar quantiser for one value by one warp (vq_func.py:175-176): argmin over n codes of
-// (x - code)^2, first minimum.  codes in global memory (n <= 256).
+// (x - code)^2, first minimum.  codes in global or shared memory (n <= 256 = 8 per lane: the loads are issued
+// together, so one memory latency is exposed instead of eight).
 template <typename T>
 __device__ __forceinline__ int warp_scl_nearest(const T *__restrict__ codes, int n, float x, int lane, T &q)
 {
+    static_assert(FPC_MAX_SCL_ENTRIES == 256, "eight codes per lane");
+    T c[8];
+#pragma unroll
+    for (int j = 0; j < 8; ++j) c[j] = lane + 32 * j < n ? codes[lane + 32 * j] : (T)0;
     T best = Rn<T>::inf();
     int bi = 0x7fffffff;
-    T xv = (T)x;
-    for (int k = lane; k < n; k += 32) {
-        T t = Rn<T>::sub(xv, codes[k]);
-        T d = Rn<T>::mul(t, t);
-        if (d < best || bi == 0x7fffffff) { best = d; bi = k; }  // ascending k per lane: first min kept
+    const T xv = (T)x;
+#pragma unroll
+    for (int j = 0; j < 8; ++j) {
+        const int k = lane + 32 * j;
+        const T t = Rn<T>::sub(xv, c[j]);
+        const T d = Rn<T>::mul(t, t);
+        if (k < n && (d < best || bi == 0x7fffffff)) { best = d; bi = k; }  // ascending k per lane: first min kept
     }
     warp_argmin(best, bi);
     if (bi == 0x7fffffff) bi = 0;

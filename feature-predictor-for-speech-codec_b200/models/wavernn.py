@@ -199,6 +199,10 @@ class Wavernn(nn.Module):
             if t.is_cuda or t.dtype != dt or tuple(t.shape) != shp or not t.is_contiguous():
                 raise ValueError("out[%r] must be a contiguous CPU %s tensor of shape %r" % (k, dt, shp))
             res[k] = t
+        older = getattr(self, "_host_keep_older", None)
+        if older is not None:
+            older[4].synchronize()           # the call before the previous one has finished: its buffers may go
+        self._host_keep_older = getattr(self, "_host_keep", None)
         with torch.cuda.device(dev):
             need = N.lib().fpc_encode_host_workspace_bytes(B, Lf, self.precision)
             ws = getattr(self, "_host_ws", None)
@@ -215,7 +219,13 @@ class Wavernn(nn.Module):
             N.check(N.lib().fpc_encode_host(weights.data_ptr(), cbs.ptr() if cbs is not None else None,
                                             ctypes.byref(io), self.precision, int(chunks), ws.data_ptr(), ws.numel(),
                                             N.current_stream(dev)), "fpc_encode_host")
-        self._host_keep = (cbs, feat, weights, res)      # keep alive until the asynchronous work has run
+            done = torch.cuda.Event()
+            done.record(torch.cuda.current_stream(dev))
+        # The copies read / write the host tensors after this call returns.  They are kept alive here for two more calls
+        # (the second of which waits on `done` before dropping them -- by then it has long completed, so the host
+        # still enqueues one call ahead of the GPU), so a caller that discards a result without synchronising cannot
+        # free pinned memory under a running DMA.
+        self._host_keep = (cbs, feat, weights, res, done)
         return res
 
     def histograms(self, res):

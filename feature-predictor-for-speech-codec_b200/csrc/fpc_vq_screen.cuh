@@ -288,7 +288,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
                     const T *crow = reinterpret_cast<const T *>(cbbase + bk.off_r[0]) + (size_t)ks * kDim;
 #pragma unroll
                     for (int d = 0; d < kDim; ++d) a = __fmaf_rn(-2.0f * xr[d], (float)crow[d], a);
-                    sval[v * kSurv + lane] = fmaxf(a + marg[2 * v + 1], 0.0f);
+                    // stored with the margin already added: the last stage uses it as is (one add, done once here)
+                    sval[v * kSurv + lane] = fmaxf(a + marg[2 * v + 1], 0.0f) + M;
                 }
                 if (lane == 0 && !ok) flag[v] = 1;
             }
@@ -332,8 +333,8 @@ __device__ __forceinline__ void vq_search_rows_screened(const PackedVq &bk_in, c
 #pragma unroll
                     for (int s2 = 0; s2 < kSurv; ++s2) {
                         if (s2 < ns) {
-                            const float bsa = two ? (sval[va * kSurv + s2] + Ma) : nxa;
-                            const float bsc = two ? (sval[vc * kSurv + s2] + Mc) : nxc;
+                            const float bsa = two ? sval[va * kSurv + s2] : nxa;
+                            const float bsc = two ? sval[vc * kSurv + s2] : nxc;
                             const int ib = (s2 << 10) | k;
                             upd2(ma1, ia, ma2, (a00 + bsa) + g.a[s2].x, ib);
                             upd2(ma1, ia, ma2, (a10 + bsa) + g.a[s2].y, ib + 1);

@@ -51,7 +51,7 @@ template <int TU> struct Smem {
     static constexpr int offMisc = offRq + MT * 20 * 4;
     // misc: m1[MT] m2[MT] (float), idx0/idx1/idx2[MT] (int), listA[MT] listB[MT] (int), counts[4]
     static constexpr int offScl = ((offMisc + (7 * MT + 4) * 4 + 15) / 16) * 16;   // both scalar tables, file dtype, 2 x 2 KB
-    static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8;
+    static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8 + 16;   // + {n, dtype} of the two scalar tables
     static constexpr int total = ((offBars + 2 * kStages * 8 + 127) / 128) * 128;
     // VQ scratch aliases the DEAD state set (the one holding the previous frame's h1/h2)
     static constexpr int kScratchBytes = kStateSet * 4;
@@ -243,6 +243,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
             for (int i = tid; i < (n0 + 7) / 8; i += kComputeThreads) reinterpret_cast<long long *>(sclbuf)[i] = src0[i];
             for (int i = tid; i < (n1 + 7) / 8; i += kComputeThreads)
                 reinterpret_cast<long long *>(sclbuf + FPC_MAX_SCL_ENTRIES * 8)[i] = src1[i];
+            if (tid == 0) {
+                int *meta = reinterpret_cast<int *>(sclbuf + 2 * FPC_MAX_SCL_ENTRIES * 8);
+                meta[0] = cbh->scl.n; meta[1] = cbh->scl.dtype; meta[2] = cbh->blscl.n; meta[3] = cbh->blscl.dtype;
+            }
         }
     }
     Pipe pp{0, 0u};
@@ -364,8 +368,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                     m2 = __shfl_sync(0xffffffffu, m2, 0);
                     int i0 = -1;
                     if (P.mode == kModeQuantize && valid) {
-                        const PackedScl &sb = (m1 != 0.0f) ? cbh->scl : cbh->blscl;
-                        const unsigned char *sclt = sclbuf + ((m1 != 0.0f) ? 0 : FPC_MAX_SCL_ENTRIES * 8);
+                        const int which = (m1 != 0.0f) ? 0 : 1;       // above / below threshold table (:217-225)
+                        const unsigned char *sclt = sclbuf + which * (FPC_MAX_SCL_ENTRIES * 8);
+                        const int *meta = reinterpret_cast<const int *>(sclbuf + 2 * FPC_MAX_SCL_ENTRIES * 8) + 2 * which;
+                        struct { int n, dtype; } sb = {meta[0], meta[1]};
                         if (sb.n > 0) {
                             const float x0 = rs[u * kLdR + 3];
                             float qv;

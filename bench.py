@@ -18,10 +18,18 @@ over ranks):
 The 328 MB input and 1.3 GB of outputs per step are larger than the 126 MB L2, so nothing is
 served from cache between steps.
 
---impl reference times the reference's algorithm on the host cores: the reference itself is pure
-Python (12 frames/s per process) and cannot travel to the GPU box, so this arm runs
-its C restatement (oracle/, OpenMP over utterances, all host threads) on a bounded sample of the
-same workload.  It is the only place besides cpu_baseline where bench.py executes oracle/.
+Every line also carries `scaling100k`: BASELINE.json configs[4], the closed-loop encode of --total-utts (100 000)
+utterances x L frames sharded by utterance over the N ranks (strong scaling, no collective, features generated on the
+device from per-chunk Philox seeds so the data set does not depend on N), with a digest of the index record and
+decoded features of 64 fixed utterance ids: equal digests across the N = 1/2/4/8 lines -- and against rank 0 encoding
+those 64 utterances alone -- show that the sharded result is bit-identical.  `calibrated` repeats the headline with
+thresholds that put about half of the frames below threshold (both codebook branches are then timed).
+
+--impl reference times the reference on the host cores: the UNMODIFIED Python reference staged under
+baseline/_ref (oracle/stage_ref.py), one process per host core through oracle/ref_worker.py (`kind: "reference"`), and
+beside it the C restatement (oracle/, OpenMP over utterances, all host threads; `port`), each on a bounded sample of
+the same workload.  When no staged reference travelled with the tree the port alone is reported (`kind: "port"`).
+These legs are the only places where bench.py executes oracle/.
 """
 import argparse
 import json
@@ -129,6 +137,82 @@ def thresholds(name):
     return (0.09, 0.28) if name == "readme" else (0.25, 2.1)
 
 
+def make_features_device(torch, dev, first, count, n_frames, chunk=1024):
+    """(count, n_frames, 20) features of utterances [first, first + count) generated on the device.  Same process as
+    fpc_synth.make_features (AR(1) cepstra with rho 0.95 and stationary std 0.3 / 0.1, piecewise-constant pitch), but
+    drawn from torch's Philox generator seeded per CHUNK of 1024 utterance ids, so utterance u has the same features
+    whatever range, rank or GPU count it is generated for (100 000 distinct utterances; the scipy generator would
+    need minutes for them)."""
+    out = torch.empty((count, n_frames, 20), dtype=torch.float32, device=dev)
+    g = torch.Generator(device=dev)
+    rho = 0.95
+    std = torch.full((18,), 0.1, device=dev)
+    std[0] = 0.3
+    sig = std * (1.0 - rho * rho) ** 0.5
+    nseg = (n_frames + 19) // 20
+    pos = first
+    while pos < first + count:
+        c = pos // chunk
+        lo = c * chunk
+        g.manual_seed(7_000_003 + c)
+        eps = torch.randn((chunk, n_frames, 18), generator=g, device=dev)
+        seg = torch.rand((chunk, nseg, 2), generator=g, device=dev) * 2.0 - 1.0
+        a, b = max(lo, first), min(lo + chunk, first + count)
+        blk = out[a - first:b - first]
+        blk[:, :, :18] = eps[a - lo:b - lo] * sig
+        blk[:, 0, :18] = eps[a - lo:b - lo, 0] * std
+        blk[:, :, 18:] = seg[a - lo:b - lo].repeat_interleave(20, dim=1)[:, :n_frames]
+        pos = lo + chunk
+    for t in range(1, n_frames):
+        out[:, t, :18].add_(out[:, t - 1, :18], alpha=rho)
+    return out
+
+
+def host_threads():
+    # every host thread this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for its children
+    try:
+        return len(os.sched_getaffinity(0))
+    except AttributeError:
+        return os.cpu_count() or 1
+
+
+def staged_reference():
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import stage_ref
+    return stage_ref.stage()        # copies from /root/reference when present (build container); else what travelled
+
+
+def python_reference_encode(n_frames, l1, l2, steps, warmup, seconds_per_step, max_procs=32):
+    """The unmodified Python reference (baseline/_ref), one single-threaded process per host core, each on its own
+    utterance.  Returns (frames/s over all processes per step list, description dict) or None."""
+    src = staged_reference()
+    if src is None:
+        return None
+    procs = max(1, min(host_threads(), max_procs))
+    env = dict(os.environ, FPC_REFERENCE_SRC=src, OMP_NUM_THREADS="1", MKL_NUM_THREADS="1")
+    cmd = [sys.executable, os.path.join(ROOT, "oracle", "ref_worker.py"), "encode"]
+    ps = [subprocess.Popen(cmd + [str(k), str(n_frames), repr(l1), repr(l2), str(steps), str(warmup), repr(seconds_per_step)],
+                           stdout=subprocess.PIPE, stderr=subprocess.PIPE, text=True, env=env) for k in range(procs)]
+    outs = []
+    for pr in ps:
+        try:
+            o, e = pr.communicate(timeout=600)
+        except subprocess.TimeoutExpired:
+            pr.kill()
+            return None
+        if pr.returncode != 0:
+            sys.stderr.write("ref_worker failed: %s\n" % e[-400:])
+            return None
+        outs.append(json.loads(o.strip().splitlines()[-1]))
+    # the processes run side by side: a step's rate is the frames all of them coded over the slowest one's time
+    rates = []
+    for k in range(steps):
+        rates.append(sum(o["frames_per_step"] for o in outs) / max(o["seconds"][k] for o in outs))
+    frames = [o["frames_per_step"] for o in outs]
+    return rates, {"cores": procs, "frames_per_process_per_step": [min(frames), max(frames)], "frames_total": sum(frames),
+                   "per_process_frames_per_s": sum(o["probe_frames_per_s"] for o in outs) / len(outs), "src": os.path.relpath(src, ROOT)}
+
+
 # ---------------------------------------------------------------------------------------------
 # reference arm / cpu baseline: the oracle port on the host cores
 # ---------------------------------------------------------------------------------------------
@@ -139,11 +223,7 @@ def cpu_encode_rate(S, n_frames, l1, l2, target_seconds, first_utt=0):
     w = O.weights_from_state_dict(sd)
     cbs = S.make_codebooks(0)
     C = O.Codebooks(cbs["cb_path"], cbs["scl_cb_path"], cbs["bl_cb_path"], cbs["bl_scl_cb_path"])
-    # every host thread this process may use -- not OMP_NUM_THREADS, which torchrun pins to 1 for its children
-    try:
-        threads = len(os.sched_getaffinity(0))
-    except AttributeError:
-        threads = os.cpu_count() or 1
+    threads = host_threads()
     probe = S.make_features(threads, min(n_frames, 50), first_utt=first_utt)
     t0 = time.perf_counter()
     O.encode(w, C, probe, l1, l2, nthreads=threads)
@@ -166,22 +246,37 @@ def run_reference(args):
     if rank != 0:
         return
     l1, l2 = thresholds(args.thresholds)
-    budget = 150.0 / max(1, args.steps + args.warmup)
-    step, n_utts, threads = cpu_encode_rate(S, args.frames, l1, l2, min(20.0, budget))
+    nsteps = max(1, args.steps + args.warmup)
+    # the C port first (short), then the real reference with what is left of a ~4 minute budget
+    step, n_utts, threads = cpu_encode_rate(S, args.frames, l1, l2, min(10.0, 60.0 / nsteps))
     for _ in range(args.warmup):
         step()
     ts = [step() for _ in range(args.steps)]
-    frames = n_utts * args.frames
-    val = frames * len(ts) / sum(ts)
-    sample = "%d utterances x %d frames per step (same generator and codebooks as the GPU arm)" % (n_utts, args.frames)
+    port_val = n_utts * args.frames * len(ts) / sum(ts)
+    port = {"value": port_val, "unit": UNIT, "cores": threads, "kind": "port", "ms_per_step": 1e3 * sum(ts) / len(ts),
+            "sample": "%d utterances x %d frames per step (same generator and codebooks as the GPU arm)" % (n_utts, args.frames),
+            "note": "C restatement of the reference (oracle/), OpenMP over utterances"}
+    ref = python_reference_encode(args.frames, l1, l2, args.steps, args.warmup, min(8.0, 150.0 / nsteps))
+    if ref is not None:
+        rates, info = ref
+        val = len(rates) / sum(1.0 / r for r in rates)        # frames over total time of the timed steps
+        fr = info["frames_per_process_per_step"]
+        cpu = {"value": val, "unit": UNIT, "cores": info["cores"], "kind": "reference",
+               "sample": "%d processes (one per host core, torch.set_num_threads(1)), each the first %d-%d frames of its own "
+                         "utterance per step" % (info["cores"], fr[0], fr[1]),
+               "note": "UNMODIFIED Python reference (%s, sha256 manifest beside it): Wavernn.encoder with its own vq_quantize / "
+                       "scl_quantize, codebooks np.load-ed per call" % info["src"],
+               "per_process_frames_per_s": info["per_process_frames_per_s"], "port": port}
+        ms = 1e3 * info["frames_total"] / val
+    else:
+        val, cpu, ms = port_val, dict(port), port["ms_per_step"]
+        cpu["note"] += "; no staged Python reference travelled with the tree (baseline/_ref absent)"
     line = {
         "impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus, "steps": args.steps,
-        "warmup": args.warmup, "ms_per_step": 1e3 * sum(ts) / len(ts), "higher_is_better": True, "scaling": "weak",
+        "warmup": args.warmup, "ms_per_step": ms, "higher_is_better": True, "scaling": "weak",
         "vs_baseline": None, "dtype": "f32", "data": "synthetic",
         "config": {"workload": workload_name(args), "thresholds": args.thresholds, "l1": l1, "l2": l2},
-        "cpu_baseline": {"value": val, "unit": UNIT, "cores": threads, "kind": "port", "sample": sample,
-                         "note": "C restatement of the reference (oracle/), OpenMP over utterances; the Python reference "
-                                 "itself ran at 12.3 frames/s per process in the build container (BASELINE.md)"},
+        "cpu_baseline": cpu,
         "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
         "gpu_launches": 0,
     }
@@ -240,7 +335,7 @@ def run_ours(args):
     def step_e2e():
         # the reference-facing call with HOST buffers: upload, closed loop and download of every result inside
         # (C ABI fpc_encode_host: time-chunked, the copies overlap the kernel)
-        return model.encode_host(cfg, feat_h, l1, l2, qtz=True, out=host_out, chunks=args.e2e_chunks)
+        return model.encode_host(cfg, feat_h, l1, l2, qtz=True, out=host_out, chunks=args.e2e_chunks, want_hist=True)
 
     with torch.no_grad():
         for _ in range(args.warmup):
@@ -280,25 +375,46 @@ def run_ours(args):
         barrier()
         e2e_ms = e0.elapsed_time(e1)
         checksum = float(host_out["c_in"][0, -1].sum())   # the result really is on the host
+        cb_tot = Wavernn.host_cb_tot(host_out)            # ... and so is the 7th element of the reference's tuple
+        e2e_hist_frames = [float(np.sum(h)) for h in cb_tot]
 
-    d2h_bytes = int(sum(v.numel() * v.element_size() for v in out.values()))
+        # ---- the same step at calibrated thresholds: about half of the frames take the below-threshold books ----
+        calibrated = None
+        if args.thresholds == "readme" and not args.no_calibrated:
+            cl1, cl2 = thresholds("calibrated")
+            for _ in range(2):
+                model.encode_device(cfg, feat_d, None, cl1, cl2, qtz=True, want_under=False, out=out)
+            barrier()
+            c0, c1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+            c0.record(stream)
+            for _ in range(args.calibrated_steps):
+                cres = model.encode_device(cfg, feat_d, None, cl1, cl2, qtz=True, want_under=False, out=out)
+            c1.record(stream)
+            barrier()
+            calibrated = {"ms": c0.elapsed_time(c1) / args.calibrated_steps, "l1": cl1, "l2": cl2,
+                          "p1": float(cres.ind1.mean().item()), "p2": float(cres.ind2.mean().item())}
+
+    d2h_bytes = int(sum(v.numel() * v.element_size() for v in out.values())) + 8 * fpc_native.HIST_TOTAL
     del host_out
+    scaling = None
+    feat_d = res = cres = None          # free the headline's device buffers before the other workloads
+    out.clear()
+    model.last_result = None
+    torch.cuda.empty_cache()
+    if args.total_utts > 0:
+        scaling = bench_scaling(args, torch, dist, dev, rank, world, barrier, model, cfg, l1, l2)
     bf16 = None
     if args.workload in ("both", "bf16"):
-        del feat_d
-        for k in list(out):
-            out[k] = out[k][:0]
-        torch.cuda.empty_cache()
         bf16 = bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, l2)
     kmeans = None
     if args.workload in ("both", "kmeans"):
         torch.cuda.empty_cache()
         kmeans = bench_kmeans(args, torch, dist, dev, rank, world, barrier)
 
-    t = torch.tensor([ms_total, e2e_ms, wall * 1e3], dtype=torch.float64, device=dev)
+    t = torch.tensor([ms_total, e2e_ms, wall * 1e3, calibrated["ms"] if calibrated else 0.0], dtype=torch.float64, device=dev)
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    ms_total, e2e_ms, wall_ms = [float(x) for x in t.tolist()]
+    ms_total, e2e_ms, wall_ms, cal_ms = [float(x) for x in t.tolist()]
     frames_all = float(U) * L * world
     value = frames_all * args.steps / (ms_total * 1e-3)
     e2e_value = frames_all * args.steps / (e2e_ms * 1e-3)
@@ -316,13 +432,17 @@ def run_ours(args):
             "dtype": "f32", "data": "synthetic",
             "config": {"workload": workload_name(args), "utterances_per_gpu": U, "frames": L, "thresholds": args.thresholds,
                        "l1": l1, "l2": l2, "above_threshold_fraction": {"c0": p1, "c1_17": p2},
+                       "inputs": "%d distinct seeded utterances per rank (fpc_synth.make_features, seed 1000 + id), tiled %dx to "
+                                 "fill the batch" % (min(U, 512), (U + min(U, 512) - 1) // min(U, 512)),
+                       "launch_plan": fpc_native.encode_plan(U, fpc_native.FPC_PREC_FP32),
                        "l2_policy": "inputs (328 MB/step) and outputs (1.3 GB/step) larger than the 126 MB L2",
                        "parallelism": "utterance shards, %d rank(s), no collective" % world},
             "e2e": {"value": e2e_value, "unit": UNIT, "ms_per_step": e2e_ms / args.steps,
                     "h2d_bytes_per_step": int(feat_h.numel() * 4),
                     "d2h_bytes_per_step": d2h_bytes,
-                    "call": "Wavernn.encode_host (fpc_encode_host), chunks=%s" % (args.e2e_chunks or "auto"),
-                    "checksum": checksum},
+                    "call": "Wavernn.encode_host (fpc_encode_host), chunks=%s; returns c_in, r, r_qtz, ind1, ind2, the index "
+                            "record and cb_tot" % (args.e2e_chunks or "auto"),
+                    "checksum": checksum, "cb_tot_frames": e2e_hist_frames},
             "gpu_launches": int(launches),
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": NCU_DRAM_BYTES_PER_FRAME * U * L,
@@ -337,14 +457,37 @@ def run_ours(args):
             "clocks": clocks,
             "wall_ms_per_step": wall_ms / args.steps,
         }
+        if calibrated is not None:
+            cf = flops_per_frame(calibrated["p1"], calibrated["p2"])
+            cach = U * L * cf / (cal_ms * 1e-3) / 1e12
+            line["calibrated"] = {
+                "workload": "the headline step at calibrated thresholds l1=%g l2=%g (SURVEY.md 8d)" % (calibrated["l1"], calibrated["l2"]),
+                "value": U * L * world / (cal_ms * 1e-3), "unit": UNIT, "ms_per_step": cal_ms, "steps": args.calibrated_steps,
+                "above_threshold_fraction": {"c0": calibrated["p1"], "c1_17": calibrated["p2"]},
+                "roofline": {"bound": "fp32", "achieved": cach, "peak": fp32_peak, "unit": "TFLOP/s", "frac": cach / fp32_peak,
+                             "flop_per_frame": cf}}
+        if scaling is not None:
+            line["scaling100k"] = scaling
         if world == 1 and not args.no_cpu_baseline:
             step, n_utts, threads = cpu_encode_rate(S, L, l1, l2, args.cpu_seconds)
             dt = step()
-            line["cpu_baseline"] = {
-                "value": n_utts * L / dt, "unit": UNIT, "cores": threads, "kind": "port",
-                "sample": "%d utterances x %d frames, one pass (%.1f s)" % (n_utts, L, dt),
-                "note": "C restatement of the reference (oracle/), OpenMP over utterances; the Python reference itself "
-                        "ran at 12.3 frames/s per process in the build container (BASELINE.md)"}
+            port = {"value": n_utts * L / dt, "unit": UNIT, "cores": threads, "kind": "port",
+                    "sample": "%d utterances x %d frames, one pass (%.1f s)" % (n_utts, L, dt),
+                    "note": "C restatement of the reference (oracle/), OpenMP over utterances"}
+            ref = python_reference_encode(L, l1, l2, 1, 0, args.cpu_seconds)
+            if ref is not None:
+                rates, info = ref
+                fr = info["frames_per_process_per_step"]
+                line["cpu_baseline"] = {
+                    "value": rates[0], "unit": UNIT, "cores": info["cores"], "kind": "reference",
+                    "sample": "%d processes (one per host core, torch.set_num_threads(1)), each the first %d-%d frames of its own "
+                              "utterance, one pass" % (info["cores"], fr[0], fr[1]),
+                    "note": "UNMODIFIED Python reference (%s): Wavernn.encoder with its own vq_quantize / scl_quantize, codebooks "
+                            "np.load-ed per call" % info["src"],
+                    "per_process_frames_per_s": info["per_process_frames_per_s"], "port": port}
+            else:
+                port["note"] += "; no staged Python reference travelled with the tree (baseline/_ref absent)"
+                line["cpu_baseline"] = port
         if bf16 is not None:
             line["bf16"] = bf16
         if kmeans is not None:
@@ -354,6 +497,87 @@ def run_ours(args):
         dist.destroy_process_group()
     tmp.cleanup()
 
+
+
+# ---------------------------------------------------------------------------------------------
+# BASELINE.json configs[4]: >= 100k utterances sharded by utterance over the ranks (strong scaling)
+# ---------------------------------------------------------------------------------------------
+DIGEST_IDS = 64
+
+
+def _utt_digest(idx_u, cin_u):
+    import hashlib
+    h = hashlib.sha256()
+    h.update(idx_u.contiguous().cpu().numpy().tobytes())
+    h.update(cin_u.contiguous().cpu().numpy().tobytes())
+    return h.hexdigest()
+
+
+def bench_scaling(args, torch, dist, dev, rank, world, barrier, model, cfg, l1, l2):
+    import hashlib
+    import fpc_dist
+    import fpc_native
+    total, L = args.total_utts, args.frames
+    first, count = fpc_dist.shard_range(total, rank, world)
+    feat = make_features_device(torch, dev, first, count, L)
+    out = {"c_in": torch.empty((count, L, 20), device=dev), "r": torch.empty((count, L, 18), device=dev),
+           "r_qtz": torch.empty((count, L, 18), device=dev), "ind1": torch.empty((count, L, 1), device=dev),
+           "ind2": torch.empty((count, L, 1), device=dev), "idx": torch.empty((count, L, 4), dtype=torch.int32, device=dev)}
+    stream = torch.cuda.current_stream(dev)
+    with torch.no_grad():
+        for _ in range(args.scaling_warmup):
+            res = model.encode_device(cfg, feat, None, l1, l2, qtz=True, want_under=False, out=out)
+        barrier()
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        n0 = fpc_native.launch_count()
+        e0.record(stream)
+        for _ in range(args.scaling_steps):
+            res = model.encode_device(cfg, feat, None, l1, l2, qtz=True, want_under=False, out=out)
+        e1.record(stream)
+        barrier()
+        launches = fpc_native.launch_count() - n0
+        t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(t, op=dist.ReduceOp.MAX)
+        ms = float(t.item()) / args.scaling_steps
+        # digest of fixed utterance ids, gathered from the ranks that own them
+        ids = [7 + k * (total // DIGEST_IDS) for k in range(DIGEST_IDS)] if total >= 8 * DIGEST_IDS else list(range(total))
+        mine = {u: _utt_digest(res.idx[u - first], res.c_in[u - first]) for u in ids if first <= u < first + count}
+        if world > 1:
+            parts = [None] * world
+            dist.all_gather_object(parts, mine)
+        else:
+            parts = [mine]
+        p2 = float(res.ind2.mean().item())
+        del res
+        model.last_result = None
+        single = None
+        if rank == 0:
+            merged = {}
+            for part in parts:
+                merged.update(part)
+            digest = hashlib.sha256("".join(merged[u] for u in ids).encode()).hexdigest()
+            # the same ids encoded ALONE by this rank (one small batch: other tiles, other plan)
+            sub = torch.cat([make_features_device(torch, dev, u, 1, L) for u in ids])
+            r1 = model.encode_device(cfg, sub, None, l1, l2, qtz=True, want_under=False)
+            torch.cuda.synchronize()
+            alone = {u: _utt_digest(r1.idx[k], r1.c_in[k]) for k, u in enumerate(ids)}
+            single = hashlib.sha256("".join(alone[u] for u in ids).encode()).hexdigest()
+    del feat, out
+    torch.cuda.empty_cache()
+    if rank != 0:
+        return None
+    return {"workload": "closed-loop encode, %d utterances x %d frames in total (BASELINE.json configs[4]), sharded by utterance "
+                        "over %d rank(s), fp32 predictor" % (total, L, world),
+            "scaling": "strong", "value": total * L / (ms * 1e-3), "unit": UNIT, "ms_per_step": ms, "steps": args.scaling_steps,
+            "warmup": args.scaling_warmup, "utterances_total": total, "utterances_rank0": count, "gpu_launches": int(launches),
+            "launch_plan_rank0": fpc_native.encode_plan(count, fpc_native.FPC_PREC_FP32),
+            "above_threshold_fraction_c1_17_rank0": p2,
+            "inputs": "device Philox generator seeded per chunk of 1024 utterance ids (bench.make_features_device): utterance u "
+                      "is the same whatever the rank count; inputs resident in HBM, no e2e leg for this workload",
+            "digest": {"ids": "%d utterance ids %d + k * %d" % (len(ids), ids[0], (ids[1] - ids[0]) if len(ids) > 1 else 0),
+                       "sharded": digest, "encoded_alone_on_rank0": single, "bit_identical": digest == single,
+                       "what": "sha256 over the (L,4) int32 index record and the (L,20) float32 decoded features of each id"}}
 
 
 # ---------------------------------------------------------------------------------------------
@@ -549,6 +773,12 @@ def main():
     ap.add_argument("--vq-train-vectors", type=int, default=2_000_000, help="sample for the full vq_train schedule (0 = skip)")
     ap.add_argument("--cpu-seconds", type=float, default=15.0)
     ap.add_argument("--e2e-chunks", type=int, default=0, help="frame ranges of the host-buffer call (0 = library default)")
+    ap.add_argument("--total-utts", type=int, default=100_000,
+                    help="utterances of the strong-scaling leg, sharded over the ranks (BASELINE.json configs[4]); 0 = skip")
+    ap.add_argument("--scaling-steps", type=int, default=2)
+    ap.add_argument("--scaling-warmup", type=int, default=1)
+    ap.add_argument("--no-calibrated", action="store_true")
+    ap.add_argument("--calibrated-steps", type=int, default=3)
     args = ap.parse_args()
     if args.warmup < 3 and args.impl == "ours":
         args.warmup = 3

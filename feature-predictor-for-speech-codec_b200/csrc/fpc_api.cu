@@ -1,4 +1,5 @@
 // fpc_api.cu -- C-ABI entry points of the encode / decode / quantiser paths (include/fpc_b200.h).
+#include <mutex>
 #include <vector>
 #include "fpc_common.cuh"
 #include "fpc_vq.cuh"
@@ -70,10 +71,12 @@ __global__ void index_histogram_kernel(const int4 *__restrict__ idx, long n, uns
     for (long i = (long)blockIdx.x * blockDim.x + threadIdx.x; i < n; i += (long)gridDim.x * blockDim.x) {
         const int4 v = idx[i];
         if (v.x >= 0 && v.x < 256) atomicAdd(&sh[((v.w & 1) ? FPC_HIST_SCL : FPC_HIST_BL_SCL) + v.x], 1u);
-        if (v.y >= 0 && v.y < 1024) atomicAdd(&sh[((v.w & 2) ? FPC_HIST_VQ1 : FPC_HIST_BL_VQ) + v.y], 1u);
-        // a two-stage below-threshold book counts its LAST stage (cb_tot[4] += cb_t[-1], :240)
-        if (v.z >= 0 && v.z < 1024) {
-            if (v.w & 2) atomicAdd(&sh[FPC_HIST_VQ2 + v.z], 1u);
+        if (v.w & 2) {        // above threshold: cb_tot[2] += cb_t[0], cb_tot[3] += cb_t[1]  (:232-234)
+            if (v.y >= 0 && v.y < 1024) atomicAdd(&sh[FPC_HIST_VQ1 + v.y], 1u);
+            if (v.z >= 0 && v.z < 1024) atomicAdd(&sh[FPC_HIST_VQ2 + v.z], 1u);
+        } else {              // below threshold: the LAST stage of the book is counted, cb_tot[4] += cb_t[-1]  (:240)
+            const int last = v.z >= 0 ? v.z : v.y;
+            if (last >= 0 && last < 1024) atomicAdd(&sh[FPC_HIST_BL_VQ + last], 1u);
         }
     }
     __syncthreads();
@@ -127,18 +130,31 @@ int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, con
     return run_encode_fp32(P, (cudaStream_t)stream, 0);
 }
 
+int fpc_encode_plan(int B, int precision, int sms, int *segments)
+{
+    if (B < 0 || !segments) return -FPC_ERR_ARG;
+    if (precision != FPC_PREC_FP32 && precision != FPC_PREC_BF16) return -FPC_ERR_UNSUPPORTED;
+    if (sms <= 0) sms = num_sms();
+    if (sms <= 0) return -FPC_ERR_CUDA;
+    return encode_plan(B, precision, sms, segments);
+}
+
 // ---- host-buffer form: time-chunked upload / compute / download pipeline ----
 namespace {
+// One copy pipeline (upload stream, download stream, events) per device, created on first use and kept for the
+// life of the process.  `busy` is recorded at the end of every call: the next call on the same device makes its
+// copy streams wait for it, so two calls that share a workspace are ordered even when they are issued on
+// different streams.  Calls on ONE device must not be issued concurrently from several host threads (the
+// mutex only protects the table, not the order of the enqueued work).
 struct HostPipe {
-    int device = -1;
     cudaStream_t s_in = nullptr, s_out = nullptr;
+    cudaEvent_t busy = nullptr;
+    bool used = false;
     std::vector<cudaEvent_t> ev;
-    int ensure(int dev, size_t nev)
+    int ensure(size_t nev)
     {
-        if (device != dev) {           // one pipeline per process and device in use; rebuilt if the device changes
-            s_in = nullptr; s_out = nullptr; ev.clear(); device = dev;
-        }
         if (!s_in) FPC_CUDA_TRY(cudaStreamCreateWithFlags(&s_in, cudaStreamNonBlocking));
+        if (!busy) FPC_CUDA_TRY(cudaEventCreateWithFlags(&busy, cudaEventDisableTiming));
         if (!s_out) FPC_CUDA_TRY(cudaStreamCreateWithFlags(&s_out, cudaStreamNonBlocking));
         while (ev.size() < nev) {
             cudaEvent_t e;
@@ -148,7 +164,8 @@ struct HostPipe {
         return FPC_OK;
     }
 };
-HostPipe g_host_pipe;
+HostPipe g_host_pipes[kMaxDevices];
+std::mutex g_host_pipe_mutex;
 const int kHostWords[8] = {20, 20, 18, 18, 18, 1, 1, 4};   // feat, c_in, r, r_qtz, r_under, ind1, ind2, idx (4-byte words per frame)
 size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 }  // namespace
@@ -159,6 +176,7 @@ size_t fpc_encode_host_workspace_bytes(int B, int L, int precision)
     size_t total = 0;
     for (int i = 0; i < 8; ++i) total += align256((size_t)B * L * kHostWords[i] * 4);
     total += align256(precision == FPC_PREC_FP32 ? encode_fp32_state_bytes(B) : encode_bf16_state_bytes(B));
+    total += align256(sizeof(unsigned long long) * FPC_HIST_TOTAL);
     return total;
 }
 
@@ -181,17 +199,25 @@ int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks
     void *dev[8];
     for (int i = 0; i < 8; ++i) { dev[i] = ws; ws += align256((size_t)B * L * kHostWords[i] * 4); }
     void *state = ws;
+    ws += align256(precision == FPC_PREC_FP32 ? encode_fp32_state_bytes(B) : encode_bf16_state_bytes(B));
+    unsigned long long *dev_hist = (unsigned long long *)ws;
     void *host_out[8] = {nullptr, io->h_c_in, io->h_r, io->h_r_qtz, io->h_r_under, io->h_ind1, io->h_ind2, io->h_idx};
 
-    int devid = 0;
-    FPC_CUDA_TRY(cudaGetDevice(&devid));
-    HostPipe &hp = g_host_pipe;
-    { const int rc = hp.ensure(devid, (size_t)2 * chunks + 2); if (rc != FPC_OK) return rc; }
+    HostPipe &hp = g_host_pipes[device_slot()];
+    {
+        std::lock_guard<std::mutex> lock(g_host_pipe_mutex);
+        const int rc = hp.ensure((size_t)2 * chunks + 3);
+        if (rc != FPC_OK) return rc;
+    }
     cudaStream_t st = (cudaStream_t)stream;
     cudaEvent_t ev_start = hp.ev[2 * chunks], ev_done = hp.ev[2 * chunks + 1];
     FPC_CUDA_TRY(cudaEventRecord(ev_start, st));            // everything queued before this call on `stream` goes first
     FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, ev_start, 0));
     FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, ev_start, 0));
+    if (hp.used) {                                          // ... and so does the previous call on this device, whatever its stream
+        FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_in, hp.busy, 0));
+        FPC_CUDA_TRY(cudaStreamWaitEvent(st, hp.busy, 0));
+    }
 
     EncodeParams P;
     P.wstream = (const float *)d_packed_weights;
@@ -231,8 +257,23 @@ int fpc_encode_host(const void *d_packed_weights, const void *d_packed_codebooks
                                            hp.s_out));
         }
     }
+    if (io->h_hist) {
+        // cb_tot (wavernn.py:189,221-240) of the whole call: counted on the device from the index record, 28 KB down
+        if (!io->qtz) {
+            FPC_CUDA_TRY(cudaMemsetAsync(dev_hist, 0, sizeof(unsigned long long) * FPC_HIST_TOTAL, st));
+        } else {
+            const int rc = fpc_index_histogram((const int32_t *)dev[7], (long)B * L, dev_hist, st);
+            if (rc != FPC_OK) return rc;
+        }
+        cudaEvent_t ev_hist = hp.ev[2 * chunks + 2];
+        FPC_CUDA_TRY(cudaEventRecord(ev_hist, st));
+        FPC_CUDA_TRY(cudaStreamWaitEvent(hp.s_out, ev_hist, 0));
+        FPC_CUDA_TRY(cudaMemcpyAsync(io->h_hist, dev_hist, sizeof(unsigned long long) * FPC_HIST_TOTAL, cudaMemcpyDeviceToHost, hp.s_out));
+    }
     FPC_CUDA_TRY(cudaEventRecord(ev_done, hp.s_out));
     FPC_CUDA_TRY(cudaStreamWaitEvent(st, ev_done, 0));     // `stream` completes only after the last download
+    FPC_CUDA_TRY(cudaEventRecord(hp.busy, st));
+    hp.used = true;
     return FPC_OK;
 }
 
@@ -273,8 +314,7 @@ int fpc_index_histogram(const int32_t *d_idx, long n_frames, unsigned long long 
 }
 
 /* stand-alone vq_quantize on a packed codebook image; `which` 0 = cfg['cb_path'] slot,
- * 1 = cfg['bl_cb_path'] slot.  (declared in the header with a raw-codebook signature; the
- * packed form is what the Python mirror binds because it caches packed images per file.) */
+ * 1 = cfg['bl_cb_path'] slot (the Python mirror caches one packed image per codebook file). */
 int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebooks, int which, int dtype, int stages,
                            void *d_q, int32_t *d_idx, void *stream)
 {
@@ -290,20 +330,14 @@ int fpc_vq_quantize_packed(const float *d_x, long n, const void *d_packed_codebo
     const size_t fixed = (size_t)(kQTile * kLdR + kQTile * 20 + 3 * kQTile) * 4;
     if (dtype == FPC_F32) {
         const size_t smem = fixed + vq_fixed_bytes<float>(kQTile) + 8 * 1024 * sizeof(float);
-        static bool cfg = false;
-        if (!cfg) {
-            FPC_CUDA_TRY(cudaFuncSetAttribute(vq_quantize_kernel<float>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cfg = true;
-        }
+        static bool cfg[kMaxDevices] = {};
+        { const int rc = ensure_dynamic_smem(vq_quantize_kernel<float>, (int)smem, cfg); if (rc != FPC_OK) return rc; }
         vq_quantize_kernel<float><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
                                                                           (float *)d_q, d_idx, (int)(smem - fixed));
     } else if (dtype == FPC_F64) {
         const size_t smem = fixed + vq_fixed_bytes<double>(kQTile) + 8 * 1024 * sizeof(double);
-        static bool cfg = false;
-        if (!cfg) {
-            FPC_CUDA_TRY(cudaFuncSetAttribute(vq_quantize_kernel<double>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-            cfg = true;
-        }
+        static bool cfg[kMaxDevices] = {};
+        { const int rc = ensure_dynamic_smem(vq_quantize_kernel<double>, (int)smem, cfg); if (rc != FPC_OK) return rc; }
         vq_quantize_kernel<double><<<grid, kComputeThreads, smem, st>>>(d_x, n, (const char *)d_packed_codebooks, which,
                                                                            (double *)d_q, d_idx, (int)(smem - fixed));
     } else {

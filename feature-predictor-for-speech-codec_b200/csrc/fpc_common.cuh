@@ -30,6 +30,29 @@ inline int cuda_fail(cudaError_t e)
         if (_e != cudaSuccess) return ::fpc::cuda_fail(_e);  \
     } while (0)
 
+// Per-device one-time state (kernel attributes, SM count, copy pipelines) is indexed by the CUDA device
+// ordinal: cudaFuncSetAttribute and the SM count are per device, and one process may drive several GPUs
+// through the C ABI.  Ordinals beyond the table share the last slot (attributes are then set every launch).
+constexpr int kMaxDevices = 64;
+inline int device_slot()
+{
+    int d = 0;
+    if (cudaGetDevice(&d) != cudaSuccess || d < 0) d = 0;
+    return d < kMaxDevices ? d : kMaxDevices - 1;
+}
+// opt-in to more than 48 KB of dynamic shared memory, once per (kernel instantiation, device)
+template <typename Kernel>
+inline int ensure_dynamic_smem(Kernel kernel, int bytes, bool (&done)[kMaxDevices])
+{
+    const int slot = device_slot();
+    if (!done[slot] || slot == kMaxDevices - 1) {
+        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, bytes);
+        if (e != cudaSuccess) return cuda_fail(e);
+        done[slot] = true;
+    }
+    return FPC_OK;
+}
+
 // ------------------------------------------------------------------------------------------
 // packed images (device memory, produced by fpc_pack_*; layouts documented in DESIGN.md 4)
 // ------------------------------------------------------------------------------------------

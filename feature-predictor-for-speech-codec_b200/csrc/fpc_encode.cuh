@@ -23,6 +23,13 @@ struct EncodeParams {
     long long *prof;        // optional debug buffer: per-phase cycle totals of CTA 0 (fpc_debug_set_phase_buffer)
 };
 
+// launch plan: consecutive utterance ranges of the batch, each with its own tile height (fpc_encode_fp32.cu)
+constexpr int kMaxSegments = 3;
+struct EncodeSegment { int height, first, count; };
+int plan_segments(int B, int sms, const int *heights, int nh, double fixed, EncodeSegment *out);
+int encode_plan(int B, int precision, int sms, int *segments);   // (height, first, count) triples; returns their number
+EncodeParams segment_params(const EncodeParams &P, int first, int count);
+
 int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu);
 size_t encode_fp32_state_bytes(int B);   // size of EncodeParams::state for a batch of B utterances
 // bf16 tensor-core predictor (fpc_encode_bf16.cu); wstream then points at the bf16 image

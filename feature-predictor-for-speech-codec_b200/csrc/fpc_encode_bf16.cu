@@ -557,21 +557,26 @@ template <int NU>
 static int launch_encode_bf16(const EncodeParams &P, int grid, cudaStream_t st)
 {
     using S = SmemB<NU>;
-    static bool configured = false;
-    if (!configured) {
-        FPC_CUDA_TRY(cudaFuncSetAttribute(encode_bf16_kernel<NU>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    { const int rc = ensure_dynamic_smem(encode_bf16_kernel<NU>, S::total, configured); if (rc != FPC_OK) return rc; }
     encode_bf16_kernel<NU><<<grid, kBThreads, S::total, st>>>(P);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
 
+static const int kHeightsBf16[2] = {64, 32};
+// per utterance: the [x(32) | h1(384)] and h2(128) bf16 rows
+static size_t state_bytes_per_tile_bf16(int nu) { return (size_t)nu * (size_t)(kXK + kH2) * 2; }
+
 size_t encode_bf16_state_bytes(int B)
 {
-    if (B <= 0) return 0;
-    // per utterance: the [x(32) | h1(384)] and h2(128) bf16 rows; tiles are padded to at most 64 utterances
-    return (size_t)(B + 64) * (size_t)(kXK + kH2) * 2;
+    const int sms = num_sms();
+    if (sms <= 0 || B <= 0) return 0;
+    EncodeSegment seg[kMaxSegments];
+    const int n = plan_segments(B, sms, kHeightsBf16, 2, 6.0, seg);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (size_t)((seg[i].count + seg[i].height - 1) / seg[i].height) * state_bytes_per_tile_bf16(seg[i].height);
+    return total;
 }
 
 int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu)
@@ -579,23 +584,27 @@ int run_encode_bf16(EncodeParams P, cudaStream_t st, int force_nu)
     if (P.f0 < 0 || P.f1 > P.L || P.f0 >= P.f1) return FPC_ERR_ARG;
     const int sms = num_sms();
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
-    int nu = force_nu;
-    if (nu <= 0) {
-        // tile height that minimises waves x per-tile cost (+6: per-frame fixed work of a tile)
-        double best = 1e30;
-        const int cand[2] = {32, 64};
-        for (int c = 0; c < 2; ++c) {
-            const int tiles = (P.B + cand[c] - 1) / cand[c];
-            const int waves = (tiles + sms - 1) / sms;
-            const double cost = (double)waves * (cand[c] + 6.0);
-            if (cost < best - 1e-9) { best = cost; nu = cand[c]; }
-        }
+    // launch plan as in the fp32 kernel (fpc_encode_fp32.cu): whole waves of 64-utterance tiles, the rest with
+    // the height that needs the fewest tile-frames
+    EncodeSegment seg[kMaxSegments];
+    int n = 1;
+    if (force_nu > 0) seg[0] = EncodeSegment{force_nu, 0, P.B};
+    else n = plan_segments(P.B, sms, kHeightsBf16, 2, 6.0, seg);
+    char *state = reinterpret_cast<char *>(P.state);
+    for (int i = 0; i < n; ++i) {
+        EncodeParams Q = segment_params(P, seg[i].first, seg[i].count);
+        const int nu = seg[i].height;
+        Q.ntiles = (Q.B + nu - 1) / nu;
+        Q.state = state;
+        if (state) state += (size_t)Q.ntiles * state_bytes_per_tile_bf16(nu);
+        const int grid = Q.ntiles < sms ? Q.ntiles : sms;
+        int rc;
+        if (nu == 32) rc = launch_encode_bf16<32>(Q, grid, st);
+        else if (nu == 64) rc = launch_encode_bf16<64>(Q, grid, st);
+        else rc = FPC_ERR_ARG;
+        if (rc != FPC_OK) return rc;
     }
-    P.ntiles = (P.B + nu - 1) / nu;
-    const int grid = P.ntiles < sms ? P.ntiles : sms;
-    if (nu == 32) return launch_encode_bf16<32>(P, grid, st);
-    if (nu == 64) return launch_encode_bf16<64>(P, grid, st);
-    return FPC_ERR_ARG;
+    return FPC_OK;
 }
 
 }  // namespace fpc

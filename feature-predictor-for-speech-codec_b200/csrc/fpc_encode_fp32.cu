@@ -493,52 +493,121 @@ template <int TU>
 static int launch_encode(const EncodeParams &P, int grid, cudaStream_t st)
 {
     using S = Smem<TU>;
-    static bool configured = false;
-    if (!configured) {
-        FPC_CUDA_TRY(cudaFuncSetAttribute(encode_fp32_kernel<TU>, cudaFuncAttributeMaxDynamicSharedMemorySize, S::total));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    { const int rc = ensure_dynamic_smem(encode_fp32_kernel<TU>, S::total, configured); if (rc != FPC_OK) return rc; }
     encode_fp32_kernel<TU><<<grid, kThreads, S::total, st>>>(P);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }
 
-static int g_num_sms = 0;
-
 int num_sms()
 {
-    if (g_num_sms == 0) {
+    static int cached[kMaxDevices] = {};
+    const int slot = device_slot();
+    if (cached[slot] == 0 || slot == kMaxDevices - 1) {
         int dev = 0, n = 0;
         if (cudaGetDevice(&dev) != cudaSuccess) return 0;
         if (cudaDeviceGetAttribute(&n, cudaDevAttrMultiProcessorCount, dev) != cudaSuccess) return 0;
-        g_num_sms = n;
+        cached[slot] = n;
     }
-    return g_num_sms;
+    return cached[slot];
 }
 
-// utterances per CTA: the tile height that minimises (waves x per-tile cost)
-static int pick_tu(int B, int sms)
+// ------------------------------------------------------------------------------------------
+// Launch plan.  Utterances are independent (wavernn.py:217,228 only loop over k), tiles of one height cost the
+// same, and a CTA owns an SM, so a launch finishes in  waves x (height + fixed)  tile-frames.  One tile height
+// for the whole batch wastes up to a wave (12 500 utterances on 148 SMs: 391 tiles of 32 = 2.64 waves run as 3).
+// The batch is therefore cut into at most kMaxSegments consecutive utterance ranges, each launched with its
+// own tile height: whole waves of the tallest tile first, then the heights that fit what is left
+// (12 500 -> 2 waves of 32 + 1 wave of 24, cost 106 instead of 114).  Every range is an ordinary launch of the
+// same kernel on offset pointers, so results do not depend on the plan.
+// ------------------------------------------------------------------------------------------
+static double plan_rest(int B, int sms, const int *heights, int nh, double fixed, int depth, EncodeSegment *out, int *nout)
 {
-    const int cand[4] = {4, 6, 7, 8};
-    int best = 4;
-    double best_cost = 1e30;
-    for (int c = 0; c < 4; ++c) {
-        const int mt = 4 * cand[c];
-        const int tiles = (B + mt - 1) / mt;
-        const int waves = (tiles + sms - 1) / sms;
-        const double cost = (double)waves * (mt + 6.0);   // +6: per-frame fixed work (barriers, selection)
-        if (cost < best_cost - 1e-9) { best_cost = cost; best = cand[c]; }
+    if (B <= 0) { *nout = 0; return 0.0; }
+    double best = 1e300;
+    EncodeSegment best_seg[kMaxSegments];
+    int best_n = 0;
+    for (int c = 0; c < nh; ++c) {
+        const int h = heights[c];
+        const long long per_wave = (long long)sms * h;
+        const int wmax = (int)((B + per_wave - 1) / per_wave);
+        // this height closes the plan ...
+        {
+            const double cost = wmax * (h + fixed);
+            if (cost < best - 1e-9) { best = cost; best_n = 1; best_seg[0] = EncodeSegment{h, 0, B}; }
+        }
+        // ... or takes w whole waves and hands the rest to another height
+        if (depth + 1 < kMaxSegments) {
+            const int wlo = depth == 0 ? (wmax - 3 > 1 ? wmax - 3 : 1) : 1;     // the bulk goes to the first segment
+            for (int w = wlo; w < wmax; ++w) {
+                const int take = (int)(w * per_wave);
+                EncodeSegment sub[kMaxSegments];
+                int nsub = 0;
+                const double cost = w * (h + fixed) + plan_rest(B - take, sms, heights, nh, fixed, depth + 1, sub, &nsub) + 0.25;
+                if (cost < best - 1e-9) {           // + 0.25 per extra launch: prefer fewer segments on near-ties
+                    best = cost; best_n = 1 + nsub;
+                    best_seg[0] = EncodeSegment{h, 0, take};
+                    for (int i = 0; i < nsub; ++i) { best_seg[1 + i] = sub[i]; best_seg[1 + i].first += take; }
+                }
+            }
+        }
     }
+    for (int i = 0; i < best_n; ++i) out[i] = best_seg[i];
+    *nout = best_n;
     return best;
 }
+
+int plan_segments(int B, int sms, const int *heights, int nh, double fixed, EncodeSegment *out)
+{
+    int n = 0;
+    plan_rest(B, sms, heights, nh, fixed, 0, out, &n);
+    return n;
+}
+
+static const int kHeightsF32[4] = {32, 28, 24, 16};
+static const int kHeightsBf16Plan[2] = {64, 32};
+
+int encode_plan(int B, int precision, int sms, int *segments)
+{
+    EncodeSegment seg[kMaxSegments];
+    const int n = precision == FPC_PREC_BF16 ? plan_segments(B, sms, kHeightsBf16Plan, 2, 6.0, seg)
+                                             : plan_segments(B, sms, kHeightsF32, 4, 6.0, seg);
+    for (int i = 0; i < n; ++i) { segments[3 * i] = seg[i].height; segments[3 * i + 1] = seg[i].first; segments[3 * i + 2] = seg[i].count; }
+    return n;
+}
+
+static size_t state_bytes_per_tile(int mt) { return (size_t)(mt * (kLd1 + kLd2) + mt * kLdX) * sizeof(float); }
 
 size_t encode_fp32_state_bytes(int B)
 {
     const int sms = num_sms();
     if (sms <= 0 || B <= 0) return 0;
-    const int mt = 4 * pick_tu(B, sms);
-    const size_t tiles = (size_t)(B + mt - 1) / mt;
-    return tiles * (size_t)(mt * (kLd1 + kLd2) + mt * kLdX) * sizeof(float);
+    EncodeSegment seg[kMaxSegments];
+    const int n = plan_segments(B, sms, kHeightsF32, 4, 6.0, seg);
+    size_t total = 0;
+    for (int i = 0; i < n; ++i) total += (size_t)((seg[i].count + seg[i].height - 1) / seg[i].height) * state_bytes_per_tile(seg[i].height);
+    return total;
+}
+
+// the launch parameters of one utterance range of the batch
+EncodeParams segment_params(const EncodeParams &P, int first, int count)
+{
+    EncodeParams Q = P;
+    const size_t fo = (size_t)first * P.L;
+    if (Q.feat) Q.feat += fo * 20;
+    if (Q.mask) Q.mask += fo * 2;
+    if (Q.rq_in) Q.rq_in += fo * kFc;
+    if (Q.pitch_in) Q.pitch_in += fo * 2;
+    if (Q.c_in) Q.c_in += fo * 20;
+    if (Q.r) Q.r += fo * kFc;
+    if (Q.r_qtz) Q.r_qtz += fo * kFc;
+    if (Q.r_under) Q.r_under += fo * kFc;
+    if (Q.ind1) Q.ind1 += fo;
+    if (Q.ind2) Q.ind2 += fo;
+    if (Q.idx) Q.idx += fo * 4;
+    Q.B = count;
+    return Q;
 }
 
 int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu)
@@ -546,17 +615,29 @@ int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu)
     if (P.f0 < 0 || P.f1 > P.L || P.f0 >= P.f1) return FPC_ERR_ARG;
     const int sms = num_sms();
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
-    const int tu = force_tu > 0 ? force_tu : pick_tu(P.B, sms);
-    const int mt = 4 * tu;
-    P.ntiles = (P.B + mt - 1) / mt;
-    const int grid = P.ntiles < sms ? P.ntiles : sms;
-    switch (tu) {
-        case 4: return launch_encode<4>(P, grid, st);
-        case 6: return launch_encode<6>(P, grid, st);
-        case 7: return launch_encode<7>(P, grid, st);
-        case 8: return launch_encode<8>(P, grid, st);
-        default: return FPC_ERR_ARG;
+    EncodeSegment seg[kMaxSegments];
+    int n = 1;
+    if (force_tu > 0) seg[0] = EncodeSegment{4 * force_tu, 0, P.B};
+    else n = plan_segments(P.B, sms, kHeightsF32, 4, 6.0, seg);
+    char *state = reinterpret_cast<char *>(P.state);
+    for (int i = 0; i < n; ++i) {
+        EncodeParams Q = segment_params(P, seg[i].first, seg[i].count);
+        const int mt = seg[i].height;
+        Q.ntiles = (Q.B + mt - 1) / mt;
+        Q.state = state;
+        if (state) state += (size_t)Q.ntiles * state_bytes_per_tile(mt);
+        const int grid = Q.ntiles < sms ? Q.ntiles : sms;
+        int rc;
+        switch (mt / 4) {
+            case 4: rc = launch_encode<4>(Q, grid, st); break;
+            case 6: rc = launch_encode<6>(Q, grid, st); break;
+            case 7: rc = launch_encode<7>(Q, grid, st); break;
+            case 8: rc = launch_encode<8>(Q, grid, st); break;
+            default: rc = FPC_ERR_ARG;
+        }
+        if (rc != FPC_OK) return rc;
     }
+    return FPC_OK;
 }
 
 }  // namespace fpc

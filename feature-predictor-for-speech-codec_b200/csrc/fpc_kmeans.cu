@@ -384,12 +384,9 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)K * kKmLd64 * 8 + (size_t)((K + kKmPad - 1) / kKmPad * kKmPad) * kKmLd32 * 4;
-    static bool configured = false;
-    if (!configured) {
-        FPC_CUDA_TRY(cudaFuncSetAttribute(kmeans_assign_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize,
-                                          (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4))));
-        configured = true;
-    }
+    static bool configured[kMaxDevices] = {};
+    { const int rc = ensure_dynamic_smem(kmeans_assign_kernel, (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4)), configured);
+      if (rc != FPC_OK) return rc; }
     long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;
     // with a workspace and a small codebook the sums go to replicated tables first (see the kernel)
@@ -403,8 +400,10 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     }
     kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
     FPC_LAUNCH_CHECK();
-    if (R > 1) kmeans_fold_kernel<<<(K * (kDim + 1) + 255) / 256, 256, 0, st>>>(acc_sums, acc_counts, R, K, d_sums, d_counts);
-    FPC_LAUNCH_CHECK();
+    if (R > 1) {
+        kmeans_fold_kernel<<<(K * (kDim + 1) + 255) / 256, 256, 0, st>>>(acc_sums, acc_counts, R, K, d_sums, d_counts);
+        FPC_LAUNCH_CHECK();
+    }
     return FPC_OK;
 }
 

@@ -10,8 +10,28 @@ import numpy as np
 
 import fpc_native as N
 
+import collections
+
 _file_cache = {}
-_image_cache = {}
+# packed device images (~10 MB each), least recently used first; a cfg whose files are rewritten gets a new
+# key (mtime), so the table is bounded: the oldest images are dropped beyond _IMAGE_CACHE_MAX entries
+_image_cache = collections.OrderedDict()
+_IMAGE_CACHE_MAX = 8
+
+
+def _image_get(key):
+    img = _image_cache.get(key)
+    if img is not None:
+        _image_cache.move_to_end(key)
+    return img
+
+
+def _image_put(key, img):
+    _image_cache[key] = img
+    while len(_image_cache) > _IMAGE_CACHE_MAX:
+        _image_cache.popitem(last=False)
+    while len(_file_cache) > 4 * _IMAGE_CACHE_MAX:
+        _file_cache.pop(next(iter(_file_cache)))
 
 
 def load_codebook_file(path):
@@ -108,10 +128,10 @@ def from_cfg(cfg, device=None):
             keys.append(None)
             arrs[name] = None
     key = (tuple(keys), str(device))
-    img = _image_cache.get(key)
+    img = _image_get(key)
     if img is None:
         img = PackedCodebooks(device=device, **arrs)
-        _image_cache[key] = img
+        _image_put(key, img)
     return img
 
 
@@ -121,10 +141,10 @@ def single(path, slot, device=None):
     device = torch.device("cuda", torch.cuda.current_device()) if device is None else torch.device(device)
     k, a = load_codebook_file(path)
     key = ((slot, k), str(device))
-    img = _image_cache.get(key)
+    img = _image_get(key)
     if img is None:
         img = PackedCodebooks(device=device, **{slot: a})
-        _image_cache[key] = img
+        _image_put(key, img)
     return img
 
 

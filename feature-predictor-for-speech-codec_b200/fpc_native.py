@@ -20,7 +20,7 @@ HIST_TOTAL = 3584
 EXPORTS = (
     "fpc_version", "fpc_status_string", "fpc_last_cuda_error", "fpc_launch_count",
     "fpc_packed_weights_bytes", "fpc_pack_weights", "fpc_packed_codebooks_bytes", "fpc_pack_codebooks",
-    "fpc_encode_workspace_bytes", "fpc_encode", "fpc_encode_host_workspace_bytes", "fpc_encode_host",
+    "fpc_encode_workspace_bytes", "fpc_encode", "fpc_encode_plan", "fpc_encode_host_workspace_bytes", "fpc_encode_host",
     "fpc_decode", "fpc_index_histogram",
     "fpc_vq_quantize_packed", "fpc_scl_quantize",
     "fpc_kmeans_workspace_bytes", "fpc_kmeans_assign_accumulate", "fpc_kmeans_finalize", "fpc_kmeans_gather",
@@ -65,7 +65,7 @@ class EncodeHostIO(ctypes.Structure):
         ("l1", ctypes.c_float), ("l2", ctypes.c_float), ("qtz", ctypes.c_int),
         ("h_c_in", ctypes.c_void_p), ("h_r", ctypes.c_void_p), ("h_r_qtz", ctypes.c_void_p),
         ("h_r_under", ctypes.c_void_p), ("h_ind1", ctypes.c_void_p), ("h_ind2", ctypes.c_void_p),
-        ("h_idx", ctypes.c_void_p),
+        ("h_idx", ctypes.c_void_p), ("h_hist", ctypes.c_void_p),
     ]
 
 
@@ -73,21 +73,36 @@ def lib_path():
     return _LIB_PATH
 
 
+def _build_if_stale():
+    """csrc/build.py compares the .so with every .cu / .cuh / header it depends on and returns at once when it is up to
+    date, so a stale binary is never loaded after an edit.  Ranks of one job (torchrun) serialise on a lock file."""
+    import fcntl
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("_fpc_csrc_build", os.path.join(_HERE, "csrc", "build.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(_HERE, "csrc", ".build.lock"), "w") as lock:
+        fcntl.flock(lock, fcntl.LOCK_EX)
+        try:
+            mod.build()
+        finally:
+            fcntl.flock(lock, fcntl.LOCK_UN)
+
+
 def lib():
-    """Loads (building in-tree first if the sources are newer / the .so is missing)."""
+    """Loads csrc/libfpc_b200.so, rebuilding it in-tree first when it is missing or older than one of its sources
+    (FPC_B200_LIB names a prebuilt library instead: no build)."""
     global _lib
     if _lib is not None:
         return _lib
-    if not os.path.exists(_LIB_PATH):
+    if not os.environ.get("FPC_B200_LIB"):
         try:
-            import importlib.util
-            spec = importlib.util.spec_from_file_location("_fpc_csrc_build", os.path.join(_HERE, "csrc", "build.py"))
-            mod = importlib.util.module_from_spec(spec)
-            spec.loader.exec_module(mod)
-            mod.build()
+            _build_if_stale()
         except Exception as exc:  # noqa: BLE001
-            raise FpcError("libfpc_b200.so is missing and could not be built (%s); there is no CPU fallback. "
-                           "Run `python __graft_entry__.py build`." % exc) from exc
+            if not os.path.exists(_LIB_PATH):
+                raise FpcError("libfpc_b200.so is missing and could not be built (%s); there is no CPU fallback. "
+                               "Run `python __graft_entry__.py build`." % exc) from exc
+            raise FpcError("libfpc_b200.so is older than its sources and could not be rebuilt (%s)" % exc) from exc
     L = ctypes.CDLL(_LIB_PATH)
     vp, ci, cl, cf, cs = ctypes.c_void_p, ctypes.c_int, ctypes.c_long, ctypes.c_float, ctypes.c_size_t
     L.fpc_version.restype = ci
@@ -103,6 +118,7 @@ def lib():
     L.fpc_encode_workspace_bytes.restype = cs
     L.fpc_encode_workspace_bytes.argtypes = [ci, ci, ci]
     L.fpc_encode.argtypes = [vp, vp, ctypes.POINTER(EncodeIO), ci, vp, cs, vp]
+    L.fpc_encode_plan.argtypes = [ci, ci, ci, ctypes.POINTER(ci)]
     L.fpc_encode_host_workspace_bytes.restype = cs
     L.fpc_encode_host_workspace_bytes.argtypes = [ci, ci, ci]
     L.fpc_encode_host.argtypes = [vp, vp, ctypes.POINTER(EncodeHostIO), ci, ci, vp, cs, vp]
@@ -137,6 +153,15 @@ def check(status, what):
         if status == 5:
             extra = " (cudaError %d)" % L.fpc_last_cuda_error()
         raise FpcError("%s failed: %s%s" % (what, msg, extra))
+
+
+def encode_plan(n_utts, precision=FPC_PREC_FP32, sms=0):
+    """[(tile height, first utterance, count), ...] -- the launches fpc_encode makes for a batch (fpc_encode_plan)."""
+    seg = (ctypes.c_int * 9)()
+    n = lib().fpc_encode_plan(int(n_utts), int(precision), int(sms), seg)
+    if n < 0:
+        check(-n, "fpc_encode_plan")
+    return [(seg[3 * i], seg[3 * i + 1], seg[3 * i + 2]) for i in range(n)]
 
 
 def launch_count():

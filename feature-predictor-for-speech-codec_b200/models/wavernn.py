@@ -57,7 +57,7 @@ class Wavernn(nn.Module):
         self._geometry = (in_features, gru_units1, gru_units2, fc_units)
         self._packed = {}          # (device, precision) -> (version key, packed image tensor)
         self.precision = N.FPC_PREC_FP32
-        self.last_result = None    # EncodeResult of the most recent encoder() call (indices live here)
+        self.last_result = None    # index record of the most recent encoder() call (EncodeResult with idx + codebooks only)
 
     # ------------------------------------------------------------------ reference: wavernn.py:63-102
     def forward(self, x: Tensor, h1=None, h2=None):
@@ -159,18 +159,22 @@ class Wavernn(nn.Module):
                                        self.precision, None, 0, N.current_stream(dev)), "fpc_encode")
         # feat / m / weights must outlive the asynchronous kernel: tie them to the result
         res.codebooks = (cbs, feat, m, weights)
-        self.last_result = res
+        # only the index record stays pinned by the module (the reference's 7-tuple has no indices; fpc_bitstream needs
+        # them) -- not the ~1 GB of float outputs of a large call
+        self.last_result = EncodeResult(idx=res.idx, codebooks=(cbs,))
         return res
 
-    def encode_host(self, cfg, feat, l1, l2, qtz=True, out=None, chunks=0, device=None, want_under=False):
+    def encode_host(self, cfg, feat, l1, l2, qtz=True, out=None, chunks=0, device=None, want_under=False, want_hist=True):
         """Host-buffer form of the closed loop: what `feat.to('cuda')` -> `encoder(...)` -> `.cpu()` of the results
         does in the reference scripts (synthesis_qtz.py:149-160, generate_qtz_features.py:55-70), as ONE call that
         cuts the utterances along time and overlaps upload, kernel and download (C ABI fpc_encode_host).
 
         feat: (B, L, 20) float32 CPU tensor (pinned memory lets the copies overlap).  out: optional dict of CPU
         tensors to fill ("c_in", "r", "r_qtz", "r_under", "ind1", "ind2", "idx"); missing ones are allocated pinned
-        ("r_under" only if want_under).  Returns the dict; the tensors are complete after
-        torch.cuda.current_stream(device).synchronize().  Bit-identical to encoder() on the same input."""
+        ("r_under" only if want_under).  With want_hist the dict also gets "hist" (the raw usage counters, pinned int64)
+        and "codebooks"; `host_cb_tot(res)` turns them into the reference's cb_tot list once the stream is synchronised.
+        Returns the dict; the tensors are complete after torch.cuda.current_stream(device).synchronize().
+        Bit-identical to encoder() on the same input."""
         N.require_cuda()
         if not isinstance(feat, torch.Tensor) or feat.is_cuda:
             raise N.FpcError("encode_host takes a CPU tensor; use encoder()/encode_device() for CUDA tensors")
@@ -216,6 +220,13 @@ class Wavernn(nn.Module):
             io.qtz = 1 if qtz else 0
             for k in shapes:
                 setattr(io, "h_" + k, res[k].data_ptr() if k in res else None)
+            if want_hist:
+                h = res.get("hist")
+                if h is None or h.dtype != torch.int64 or h.numel() != N.HIST_TOTAL or h.is_cuda:
+                    h = torch.zeros(N.HIST_TOTAL, dtype=torch.int64).pin_memory()
+                res["hist"] = h
+                res["codebooks"] = cbs
+                io.h_hist = h.data_ptr()
             N.check(N.lib().fpc_encode_host(weights.data_ptr(), cbs.ptr() if cbs is not None else None,
                                             ctypes.byref(io), self.precision, int(chunks), ws.data_ptr(), ws.numel(),
                                             N.current_stream(dev)), "fpc_encode_host")
@@ -227,6 +238,18 @@ class Wavernn(nn.Module):
         # free pinned memory under a running DMA.
         self._host_keep = (cbs, feat, weights, res, done)
         return res
+
+    @staticmethod
+    def host_cb_tot(res):
+        """cb_tot (wavernn.py:189,221-240) of an encode_host() result; call after synchronising the stream."""
+        cbs, h = res.get("codebooks"), res["hist"].numpy()
+        if cbs is None:
+            return [0, 0, 0, 0, 0]
+        out = []
+        for off, n in zip(N.HIST_OFFSETS, cbs.hist_sizes()):
+            t = h[off:off + n].astype(np.float64)
+            out.append(t if (n > 0 and t.sum() > 0) else 0)
+        return out
 
     def histograms(self, res):
         """cb_tot (wavernn.py:189,221-240): five usage tables from the index record."""

@@ -157,6 +157,19 @@ size_t fpc_encode_workspace_bytes(int B, int L, int precision);
 int fpc_encode(const void *d_packed_weights, const void *d_packed_codebooks, const fpc_encode_io *io,
                int precision, void *d_workspace, size_t workspace_bytes, void *stream);
 
+/* The launch plan fpc_encode uses for a batch of B utterances on a device with `sms` multiprocessors (sms <= 0: the
+ * current device): up to 3 consecutive utterance ranges, each launched with its own tile height (utterances per
+ * CTA) so that no partial wave of tall tiles is left (utterances are independent, wavernn.py:217,228, so results do
+ * not depend on the plan).  Writes (tile height, first utterance, count) triples to `segments` (room for 9 ints) and
+ * returns their number, or a negative status.  Host-only arithmetic; no CUDA call when sms > 0. */
+int fpc_encode_plan(int B, int precision, int sms, int *segments);
+
+/* Threading: the library keeps per-device one-time state (kernel attributes, SM count, the copy pipeline of
+ * fpc_encode_host) indexed by the CUDA device current at the call, so one process may drive several GPUs.  Calls for
+ * DIFFERENT devices may come from different host threads; calls for the same device must be issued from one thread
+ * at a time.  fpc_encode_host orders itself after the previous fpc_encode_host call on the same device even when
+ * the two calls use different streams (they may share a workspace). */
+
 /* ---- host-buffer form of the closed loop ------------------------------------------------------------------------
  * Replaces the reference's host sequence  feat.to('cuda') -> model_f.encoder(...) -> results .cpu()
  * (synthesis_qtz.py:149-160, generate_qtz_features.py:55-70) for callers whose features and results live in host
@@ -178,6 +191,7 @@ typedef struct fpc_encode_host_io {
     float *h_ind1;         /* (B, L) */
     float *h_ind2;         /* (B, L) */
     int32_t *h_idx;        /* (B, L, 4) */
+    unsigned long long *h_hist;   /* FPC_HIST_TOTAL counters: cb_tot of the call (layout: fpc_index_histogram); may be NULL */
 } fpc_encode_host_io;
 
 /* device scratch fpc_encode_host needs: the device copies of the input, of every output, and the carried state */

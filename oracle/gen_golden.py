@@ -40,7 +40,11 @@ def sd_checksum(sd):
 
 
 def run_encoder_case(name, B, L, l1, l2, cb_dtype=np.float32, below=True, qtz=True, mask=None,
-                     first_utt=0, k_above=1024, k_below=512):
+                     first_utt=0, k_above=1024, k_below=512, compact=False):
+    """compact=True (the >= 10^4-frame cases): the features are not stored -- tests regenerate them from
+    fpc_synth.make_features(B, L, first_utt) and check feat_sha256 -- and neither are r_under (all zero when
+    qtz, wavernn.py:245-249) and r (= feat - (c_in - r_qtz) only up to rounding, so the tests compare c_in and
+    r_qtz); this keeps a 12 x 1000-frame fixture near 2 MB."""
     import torch
     W, vq_func, _ = ref_shim.load_reference()
     sd = S.make_state_dict(0)
@@ -100,11 +104,20 @@ def run_encoder_case(name, B, L, l1, l2, cb_dtype=np.float32, below=True, qtz=Tr
     for j, h in enumerate(cb_tot):
         hist["hist%d" % j] = np.asarray(h, dtype=np.float64)
     out = dict(
-        feat=feat, l1=np.float64(l1), l2=np.float64(l2), qtz=np.int32(qtz), below=np.int32(below),
+        l1=np.float64(l1), l2=np.float64(l2), qtz=np.int32(qtz), below=np.int32(below),
         cb_dtype=np.array(np.dtype(cb_dtype).name), k_above=np.int32(k_above), k_below=np.int32(k_below),
         weights_sha256=np.array(sd_checksum(sd)),
-        c_in=c_in.numpy(), r=r.numpy(), r_qtz=r_qtz.numpy(), r_under=r_under.numpy(),
+        c_in=c_in.numpy(), r_qtz=r_qtz.numpy(),
         ind1=i1n, ind2=i2n, idx=idx, ref_seconds=np.float64(dt), **hist)
+    if compact:
+        assert qtz and not r_under.numpy().any()
+        out.update(B=np.int32(B), L=np.int32(L), first_utt=np.int32(first_utt),
+                   feat_sha256=np.array(hashlib.sha256(np.ascontiguousarray(feat).tobytes()).hexdigest()))
+        out["idx"] = idx.astype(np.int16)
+        out["ind1"] = i1n.astype(np.uint8)
+        out["ind2"] = i2n.astype(np.uint8)
+    else:
+        out.update(feat=feat, r=r.numpy(), r_under=r_under.numpy())
     if mask is not None:
         out["mask"] = mask
     np.savez_compressed(os.path.join(GOLDEN, name + ".npz"), **out)
@@ -233,6 +246,10 @@ CASES = {
         "mask_b1", 1, 60, 0.25, 2.1, qtz=False, first_utt=50,
         mask=(np.random.Generator(np.random.Philox(key=9)).uniform(0, 1, (1, 60, 2)) > 0.5).astype(np.float32)),
     "smallcb": lambda: run_encoder_case("smallcb", 4, 150, 0.25, 2.1, first_utt=60, k_above=32, k_below=16),
+    # >= 10^4 coded frames of the unmodified reference per threshold pair (one mismatch = 0.008 %):
+    # 12 utterances x 10 s, the frame count of BASELINE.json configs[1]
+    "long_readme": lambda: run_encoder_case("long_readme", 12, 1000, S.L1_README, S.L2_README, first_utt=100, compact=True),
+    "long_calibrated": lambda: run_encoder_case("long_calibrated", 12, 1000, 0.25, 2.1, first_utt=200, compact=True),
 }
 
 if __name__ == "__main__":

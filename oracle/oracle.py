@@ -188,8 +188,10 @@ def histograms(idx, cbs):
     sizes = cbs.hist_sizes()
     above1 = (idx[:, 3] & 1) != 0
     above2 = (idx[:, 3] & 2) != 0
+    # below threshold the LAST stage of the book is counted: cb_tot[4] += cb_t[-1] (wavernn.py:240)
+    below_last = np.where(idx[~above2, 2] >= 0, idx[~above2, 2], idx[~above2, 1])
     sel = [(idx[above1, 0], sizes[0]), (idx[~above1, 0], sizes[1]), (idx[above2, 1], sizes[2]),
-           (idx[above2, 2], sizes[3]), (idx[~above2, 1], sizes[4])]
+           (idx[above2, 2], sizes[3]), (below_last, sizes[4])]
     out = []
     for v, n in sel:
         v = v[v >= 0]

@@ -8,9 +8,12 @@ What is required and tested:
     same bf16 recurrence, which is what a codec needs);
   * the quantiser arithmetic stays exact: every coded residual is the exact codeword the reference's
     search would pick FOR THE RESIDUAL THE KERNEL SAW (checked by re-quantising r with the oracle);
-  * stated tolerance against the fp32 oracle: predictor output within 3e-2 abs while the inputs are
-    still identical (frame 0 .. first index divergence), teacher-forced residual mode within 3e-2 abs.
-The measured index agreement is printed (and recorded in DESIGN.md), not asserted beyond a floor.
+  * stated tolerance against the fp32 oracle (the bf16 mode's contract): predictor output
+    within 3e-3 abs while the inputs are still identical (frame 0 .. first index divergence; measured 8e-4),
+    teacher-forced residuals within 3e-3, index agreement with the fp32 oracle >= 0.95 of frames at the calibrated
+    thresholds and >= 0.93 at the README thresholds (measured 0.984 / 0.968 over 64 x 200 frames), decoded
+    features within 0.05 rms of the fp32 path's;
+  * the same floors on a sample of a 16 384-utterance batch (BASELINE.json configs[2]).
 """
 import os
 import tempfile
@@ -21,7 +24,9 @@ import pytest
 from helpers import oracle_codebooks
 
 pytestmark = pytest.mark.gpu
-PRED_TOL = 3e-2
+PRED_TOL = 3e-3
+AGREE_FLOOR = {"calibrated": 0.95, "README": 0.93}
+RMS_TOL = 0.05
 
 
 @pytest.fixture(scope="module")
@@ -115,12 +120,42 @@ def test_bf16_vs_fp32_oracle_tolerance(torch_cuda, model16, synth, cfgdir, oracl
               % (name, same.mean(), int(np.median(first_div)), err[ok].max(), np.sqrt(np.mean((g["c_in"] - o["c_in"]) ** 2))))
         assert err[ok].max() <= PRED_TOL
         assert same[:, 0].mean() >= 0.8       # frame 0: identical (zero) state, only bf16 weight rounding
+        assert same.mean() >= AGREE_FLOOR[name], "bf16 index agreement %.4f below the stated floor" % same.mean()
+        assert np.sqrt(np.mean((g["c_in"] - o["c_in"]) ** 2)) <= RMS_TOL
     # teacher-forced flavour: residual generation mode feeds back feat itself whenever above threshold
     g = encode(torch, model16, {}, feat, 0.0, 0.0, qtz=False)
     o = oracle.encode(oracle_weights, None, feat, 0.0, 0.0, qtz=False)
     err = np.abs(g["r"] - o["r"]).max()
     print("bf16 residual mode (all frames above threshold => teacher forced): max abs residual diff %.3g" % err)
     assert err <= PRED_TOL
+
+
+def test_bf16_full_batch_sample(torch_cuda, model16, synth, cfgdir, oracle, oracle_weights):
+    """BASELINE.json configs[2] batch size: 16 384 utterances per GPU (100 frames here; the fp32 oracle covers a sample).
+    (a) sampled utterances equal the same utterances encoded alone -- other tiles, other launch plan; (b) the stated
+    index-agreement floor against the fp32 oracle holds on the sample; (c) decode(encode(x)) == c_in on the whole batch."""
+    torch = torch_cuda
+    cfg, cbs = cfgdir
+    B, L = 16384, 100
+    base = synth.make_features(256, L, first_utt=8300)
+    feat = np.ascontiguousarray(np.tile(base, (B // 256, 1, 1)))
+    sample = [0, 63, 64, 8191, 9471, 9472, 9473, 16383] + list(range(1000, 1024))
+    for u in sample:
+        feat[u] = synth.make_features(1, L, first_utt=20000 + u)[0]
+    fd = torch.from_numpy(feat).cuda()
+    with torch.no_grad():
+        out = model16.encoder(cfg, fd, None, 0.25, 2.1, None, None, True)
+    idx_big = model16.last_result.idx.cpu().numpy()
+    small = encode(torch, model16, cfg, feat[sample], 0.25, 2.1)
+    assert np.array_equal(small["idx"], idx_big[sample])
+    assert np.array_equal(small["c_in"], out[0][sample].cpu().numpy())
+    o = oracle.encode(oracle_weights, oracle_codebooks(oracle, cbs), feat[sample], 0.25, 2.1)
+    same = np.all(small["idx"] == o["idx"], axis=-1)
+    print("\nbf16, 16 384-utterance batch: index agreement with the fp32 oracle on %d sampled utterances x %d frames: %.4f"
+          % (len(sample), L, same.mean()))
+    assert same.mean() >= AGREE_FLOOR["calibrated"]
+    dec = model16.decoder(cfg, fd, out[2])
+    assert torch.equal(dec, out[0])
 
 
 @pytest.mark.parametrize("B,L,chunks", [(70, 40, 3), (200, 24, 0), (5, 9, 4)])

@@ -95,6 +95,56 @@ def test_encoder_vs_reference_golden_and_oracle(torch_cuda, model, oracle, oracl
     assert_bit_exact(gpu, ora, qtz)
 
 
+@pytest.mark.parametrize("case", ["long_readme", "long_calibrated"])
+def test_encoder_vs_reference_long_golden(torch_cuda, model, oracle, oracle_weights, synth, cbdir, case):
+    """>= 10^4 coded frames of the UNMODIFIED reference per threshold pair (12 utterances x 1000 frames, the frame count
+    of BASELINE.json configs[1]): the north-star bars -- indices equal on >= 99.99 % of frames, decoded features within
+    1e-4 -- and bit-exactness against the oracle over the whole 10 s recurrence."""
+    import hashlib
+    g = load_golden(case)
+    B, L = int(g["B"]), int(g["L"])
+    feat = synth.make_features(B, L, first_utt=int(g["first_utt"]))
+    assert hashlib.sha256(np.ascontiguousarray(feat).tobytes()).hexdigest() == str(g["feat_sha256"])
+    cbs = golden_codebooks(synth, g)
+    cfg = synth.save_codebooks(cbs, os.path.join(cbdir, case))
+    gpu = run_gpu(torch_cuda, model, cfg, feat, float(g["l1"]), float(g["l2"]))
+    agree, same = index_agreement(gpu["idx"], g["idx"].astype(np.int32))
+    assert agree >= INDEX_AGREEMENT, "index agreement with the reference %.6f over %d frames" % (agree, B * L)
+    for k in ("c_in", "r_qtz"):
+        err = np.abs(gpu[k] - g[k]).max()
+        assert err <= FEATURE_TOL, "%s: max abs err vs reference %g" % (k, err)
+    assert np.array_equal(gpu["ind1"], g["ind1"].astype(np.float32)) and np.array_equal(gpu["ind2"], g["ind2"].astype(np.float32))
+    if agree == 1.0:
+        assert hist_equal(gpu["cb_tot"], [g["hist%d" % j] for j in range(5)])
+        assert np.array_equal(gpu["r_qtz"], g["r_qtz"])
+    ora = oracle.encode(oracle_weights, oracle_codebooks(oracle, cbs), feat, float(g["l1"]), float(g["l2"]))
+    assert_bit_exact(gpu, ora)
+
+
+def test_launch_plan_is_invisible(torch_cuda, model, synth, cbdir):
+    """A batch that the launch plan cuts into utterance ranges with different tile heights (fpc_encode_plan) gives,
+    for every utterance, the bits that utterance gets when encoded in a small batch of its own."""
+    import fpc_native
+    torch = torch_cuda
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, L = 32 * sms + 1, 6                     # one utterance more than a full wave of the tallest tile
+    plan = fpc_native.encode_plan(B)
+    assert len(plan) >= 2 and sum(c for _, _, c in plan) == B
+    cfg = synth.save_codebooks(synth.make_codebooks(0), os.path.join(cbdir, "plan"))
+    base = synth.make_features(300, L, first_utt=7300)
+    feat = np.ascontiguousarray(np.tile(base, ((B + 299) // 300, 1, 1))[:B])
+    big = run_gpu(torch, model, cfg, feat, 0.25, 2.1)
+    edges = sorted({0, B - 1} | {f for _, f, _ in plan} | {f + c - 1 for _, f, c in plan} | {f - 1 for _, f, _ in plan if f})
+    small = run_gpu(torch, model, cfg, feat[edges], 0.25, 2.1)
+    for k in ("idx", "c_in", "r", "r_qtz", "ind1", "ind2"):
+        assert np.array_equal(small[k], big[k][edges]), k
+    # every utterance with the same features must carry the same bits, whichever range / tile it landed in
+    for k in ("idx", "c_in"):
+        ref = big[k][:300]
+        for s in range(300, B, 300):
+            assert np.array_equal(big[k][s:s + 300], ref[:min(300, B - s)]), (k, s)
+
+
 @pytest.mark.parametrize("B,L,l1,l2,dtype", [
     (1, 1, 0.25, 2.1, np.float32),        # smallest possible call
     (70, 40, 0.25, 2.1, np.float32),      # ragged: not a multiple of any tile height
@@ -194,7 +244,8 @@ def test_decoder_round_trip(torch_cuda, model, synth, cbdir):
     assert torch.equal(dec, c_in)
 
 
-def test_full_size_properties(torch_cuda, model, oracle, oracle_weights, synth, cbdir):
+@pytest.mark.parametrize("l1,l2", [(0.25, 2.1), (0.09, 0.28)])     # calibrated, and the README pair bench.py times
+def test_full_size_properties(torch_cuda, model, oracle, oracle_weights, synth, cbdir, l1, l2):
     """BASELINE.json configs[1]: 4096 utterances x 10 s on one GPU.  The oracle cannot cover 4.1 M
     frames in seconds, so: (a) utterances are independent -> a sample of them must equal the
     oracle bit for bit; (b) the same sample encoded alone (a different tiling) must equal its rows
@@ -213,7 +264,6 @@ def test_full_size_properties(torch_cuda, model, oracle, oracle_weights, synth, 
         feat[s:s + 256] = base
     for u in sample:
         feat[u] = synth.make_features(1, L, first_utt=u)[0]
-    l1, l2 = 0.25, 2.1
     fd = torch.from_numpy(feat).cuda()
     with torch.no_grad():
         out = model.encoder(cfg, fd, None, l1, l2, None, None, True)

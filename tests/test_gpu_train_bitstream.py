@@ -99,6 +99,30 @@ def test_stage_residual_and_train_stages(torch_cuda, synth, oracle):
     assert e2 < e1
 
 
+def test_train_stages_later_batches_vs_oracle(torch_cuda, synth, oracle):
+    """train_cb.py:205-211 -- every batch after the first: for each stage ten `update` calls on the incoming
+    codebook, then r = quantize(cb, r) - r feeds the next stage.  Restated here with the oracle's update / find_nearest
+    (next-stage data rounded to float32 as the product does, fpc_train.py) and compared codebook by codebook."""
+    import fpc_train
+    torch = torch_cuda
+    data = synth.make_kmeans_data(30000, seed=9, n_components=96)
+    rng = np.random.RandomState(5)
+    cb_in = [rng.randn(32, 17) * 0.1, rng.randn(16, 17) * 0.03]
+    d = torch.from_numpy(np.ascontiguousarray(data, dtype=np.float32)).cuda()
+    got = fpc_train.train_stages(d, [32, 16], codebooks=cb_in, first_batch=False)
+    r = np.ascontiguousarray(data, dtype=np.float32)
+    for i, K in enumerate((32, 16)):
+        cb = np.array(cb_in[i], dtype=np.float64)
+        for _ in range(10):
+            cb = oracle.kmeans_update(r, cb)
+        np.testing.assert_allclose(got[i], cb, rtol=1e-9, atol=1e-300, err_msg="stage %d" % i)
+        idx = oracle.find_nearest(r, cb)
+        r = (cb[idx] - r).astype(np.float32)
+    # the incoming codebooks were used: a different start gives a different result
+    other = fpc_train.train_stages(d, [32, 16], codebooks=[c[::-1].copy() * 1.5 for c in cb_in], first_batch=False)
+    assert not np.allclose(other[0], got[0])
+
+
 def test_scalar_codebook_is_a_lloyd_fixed_point(torch_cuda):
     import fpc_train
     torch = torch_cuda

@@ -92,6 +92,37 @@ def test_forward_matches_oracle_cpu(oracle, oracle_weights, state_dict, synth):
     assert np.abs(y.numpy() - yo).max() < 2e-6 and np.abs(h1.numpy()[0] - h1o).max() < 2e-6
 
 
+def test_encode_launch_plan_covers_the_batch():
+    """fpc_encode_plan (host arithmetic, no CUDA call when the SM count is given): consecutive utterance ranges that
+    cover the batch exactly once with supported tile heights; the BASELINE.json configs[4] shard (12 500 utterances on
+    148 SMs) must not be rounded up to whole waves of the tallest tile."""
+    import fpc_native
+    for prec, heights in ((fpc_native.FPC_PREC_FP32, (16, 24, 28, 32)), (fpc_native.FPC_PREC_BF16, (32, 64))):
+        for B in (1, 3, 31, 148 * 32, 148 * 32 + 1, 4096, 12500, 16384, 50000, 100000):
+            plan = fpc_native.encode_plan(B, prec, 148)
+            assert 1 <= len(plan) <= 3
+            pos = 0
+            for h, first, count in plan:
+                assert h in heights and first == pos and count > 0
+                pos += count
+            assert pos == B
+    cost = lambda plan: sum(-(-(-(-c // h)) // 148) * (h + 6) for h, _, c in plan)   # waves x (tile height + fixed)
+    assert cost(fpc_native.encode_plan(12500, fpc_native.FPC_PREC_FP32, 148)) <= 106    # 3 waves of 32 would be 114
+    assert fpc_native.encode_plan(4096, fpc_native.FPC_PREC_FP32, 148) == [(28, 0, 4096)]
+    with pytest.raises(fpc_native.FpcError):
+        fpc_native.encode_plan(-1, fpc_native.FPC_PREC_FP32, 148)
+
+
+def test_below_threshold_histogram_counts_the_last_stage(oracle):
+    """cb_tot[4] += cb_t[-1] (wavernn.py:240): with a TWO-stage below-threshold book the table counts stage-2 indices."""
+    cb2 = np.zeros((2, 8, 17), np.float32)
+    C = oracle.Codebooks(cb2, np.zeros((4, 1), np.float32), cb2, np.zeros((4, 1), np.float32))
+    idx = np.array([[[1, 5, 6, 3]], [[2, 3, 7, 1]], [[0, 2, 4, 0]]], np.int32)     # flags: above/above, c0 only, below/below
+    h = oracle.histograms(idx, C)
+    assert h[2][5] == 1 and h[3][6] == 1                  # above: both stages counted
+    assert h[4][7] == 1 and h[4][4] == 1 and h[4].sum() == 2 and h[4][3] == 0 and h[4][2] == 0
+
+
 def test_shard_range():
     import fpc_dist
     for n in (0, 1, 7, 4096, 100000):

@@ -83,3 +83,28 @@ def test_encoder_matches_reference(oracle, oracle_weights, state_dict, synth, ca
         assert hist_equal(oracle.histograms(out["idx"], C), ref_hist)
         # with identical indices the quantized residual is the same codeword sum, bit for bit
         assert np.array_equal(out["r_qtz"], g["r_qtz"])
+
+
+@pytest.mark.parametrize("case", ["long_readme", "long_calibrated"])
+def test_encoder_matches_reference_long(oracle, oracle_weights, state_dict, synth, case):
+    """>= 10^4 coded frames of the unmodified reference per threshold pair (12 x 1000 frames): one
+    mismatching frame would already be 0.008 %.  The features are regenerated from their seed (checksum in the fixture)."""
+    import hashlib
+    g = load_golden(case)
+    assert str(g["weights_sha256"]) == sd_checksum(state_dict)
+    B, L = int(g["B"]), int(g["L"])
+    assert B * L >= 10000
+    feat = synth.make_features(B, L, first_utt=int(g["first_utt"]))
+    assert hashlib.sha256(np.ascontiguousarray(feat).tobytes()).hexdigest() == str(g["feat_sha256"])
+    cbs = golden_codebooks(synth, g)
+    C = oracle_codebooks(oracle, cbs)
+    out = oracle.encode(oracle_weights, C, feat, float(g["l1"]), float(g["l2"]))
+    agree, same = index_agreement(out["idx"], g["idx"].astype(np.int32))
+    assert agree >= INDEX_AGREEMENT, "index agreement %.6f over %d frames" % (agree, B * L)
+    for k in ("c_in", "r_qtz"):
+        err = np.abs(out[k] - g[k]).max()
+        assert err <= FEATURE_TOL, "%s max abs err %g" % (k, err)
+    assert np.array_equal(out["ind1"], g["ind1"].astype(np.float32)) and np.array_equal(out["ind2"], g["ind2"].astype(np.float32))
+    if agree == 1.0:
+        assert hist_equal(oracle.histograms(out["idx"], C), [g["hist%d" % j] for j in range(5)])
+        assert np.array_equal(out["r_qtz"], g["r_qtz"])

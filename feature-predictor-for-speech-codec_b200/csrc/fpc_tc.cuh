@@ -1,0 +1,199 @@
+// fpc_tc.cuh -- nearest-codeword SCREENING on the 5th-generation tensor cores.
+//
+// The searches of this library (quantize_mstage, /root/reference/src/quantization/vq_func.py:82-131, and find_nearest,
+// quantization/cb_func.py:56-68) are contractions  score[v][k] = ||c_k||^2 - 2 <x_v, c_k>  (N x 17 . 17 x K) followed by a
+// minimum.  The decision itself must be the reference's (float64 / float32 direct-form distances in numpy's rounding
+// order), so the tensor cores only SCREEN: they produce every score to within a proven error, a scan of the
+// accumulators finds the smallest score and the runner-up of every vector, and a vector whose runner-up is more than
+// a margin away is decided; the others go to the exact code paths.
+//
+// Operand format.  tcgen05.mma.kind::f16 multiplies fp16 pairs exactly (11 + 11 significand bits fit fp32) and
+// accumulates in fp32, so a 22-bit value is carried as a (hi, lo) pair of fp16 and a product as three terms:
+//     x c  ~  xh ch + xh cl + xl ch          (dropped: xl cl <= 2^-22 |x c|)
+// Per dimension d the K extent holds   A side (vectors): xh, xh, xl    B side (codewords): ch, cl, ch
+// i.e. 51 entries for 17 dimensions; entries 51..53 carry the norm: A side 1, 1, 1; B side the 3-way fp16 split of
+// beta^2 ||c||^2; entries 54..63 are zero.  K = 64 = four tcgen05 K-slabs, 128 bytes per row.
+// Values are scaled by a power of two beta (exact) so that the largest |c| lies in [4, 8): fp16 then keeps an absolute
+// resolution of 2^-25 (subnormal hi/lo parts included), far below the 2^-22 relative target at that scale, and the
+// vector side  -2 beta x  may be up to 1024 (an x 128 times the largest codeword entry) before it leaves the format --
+// such rows are handed to the exact path.  Scores come out scaled by beta^2.
+//
+// Error of a screened score against the real value, with u = 2^-24 and R = (||x|| + Cmax)^2:
+//     fp16 pair representation of x and c:   2 * 2^-22 ||x|| ||c|| * 2   <=  4 u R       (||x|| ||c|| <= R / 4)
+//     dropped lo * lo term:                   2^-22 ||x|| ||c|| * 2       <=  2 u R
+//     absolute 2^-25 floor of the format:     <= 2 u R at the chosen scale
+//     fp32 rounding of beta c (float64 books) and the 3-way norm split:   <=  2 u R
+//     accumulation inside the tensor core:    measured by fpc_selftest_tc_scores against float64
+// The margins used by the callers (2^-15 R) leave two orders of magnitude for the last item.
+//
+// Tile layout in shared memory: "K-major, no swizzle" (fpc_umma.cuh) with R = 128 rows per tile,
+//     byte offset(r, k) = (k / 8) * 2048 + r * 16 + (k % 8) * 2,   16 KB per 128 x 64 tile, 4 KB per K-slab.
+#pragma once
+#include <cuda_fp16.h>
+
+#include "fpc_common.cuh"
+#include "fpc_umma.cuh"
+
+namespace fpc {
+namespace tc {
+
+constexpr int kK = 64;                         // K extent of both operands
+constexpr int kTileRows = 128;
+constexpr int kTileBytes = kTileRows * kK * 2; // 16384
+constexpr int kSlabBytes = kTileBytes / 4;     // one K = 16 slab of a tile
+constexpr float kMaxScaledX = 1024.0f;         // |(-2 beta x)_d| beyond this leaves the proven range
+constexpr float kPadNorm = 65504.0f;           // norm entries of padding codewords (three of them: 196 512, above any real score)
+
+// instruction descriptor: fp16 x fp16 -> f32, A and B K-major, dense
+__host__ __device__ constexpr uint32_t instr_desc_f16(uint32_t M, uint32_t N)
+{
+    return (1u << 4) | ((N >> 3) << 17) | ((M >> 4) << 24);
+}
+
+__device__ __forceinline__ void mma_f16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    umma::mma_bf16(tmem_d, adesc, bdesc, idesc, accumulate);      // same instruction; the operand type lives in idesc
+}
+
+// beta = 2^e with  4 <= beta * cmax_abs < 8  (cmax_abs = largest |c| entry of the book; 1 for an all-zero book)
+__host__ __device__ inline float scale_for(float cmax_abs)
+{
+    if (!(cmax_abs > 0.0f) || !(cmax_abs < 1e30f)) return 1.0f;
+    int e;
+    frexpf(cmax_abs, &e);                 // cmax_abs = m * 2^e, m in [0.5, 1)
+    return ldexpf(1.0f, 3 - e);           // beta * cmax_abs = 8 m in [4, 8)
+}
+
+__device__ __forceinline__ uint32_t pack_h2(__half a, __half b)
+{
+    return (uint32_t)__half_as_ushort(a) | ((uint32_t)__half_as_ushort(b) << 16);
+}
+
+// (hi, lo) fp16 pair of an fp32 value: hi = rn(v), lo = rn(v - hi) (the subtraction is exact)
+__device__ __forceinline__ void split2(float v, __half &hi, __half &lo)
+{
+    hi = __float2half_rn(v);
+    lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
+}
+
+// Writes row r of a 128-row operand tile from the 17 scaled values xs (vector side: -2 beta x; codeword side: beta c)
+// and the three norm entries (vector side: 1, 1, 1; codeword side: split of beta^2 ||c||^2).
+template <bool kVectorSide>
+__device__ __forceinline__ void store_row(unsigned char *tile, int r, const float (&xs)[kDim], __half n0, __half n1, __half n2)
+{
+    __half e[kK];
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) {
+        __half hi, lo;
+        split2(xs[d], hi, lo);
+        e[3 * d] = hi;
+        e[3 * d + 1] = kVectorSide ? hi : lo;
+        e[3 * d + 2] = kVectorSide ? lo : hi;
+    }
+    e[51] = n0; e[52] = n1; e[53] = n2;
+#pragma unroll
+    for (int i = 54; i < kK; ++i) e[i] = __float2half_rn(0.0f);
+#pragma unroll
+    for (int c = 0; c < kK / 8; ++c) {
+        uint4 w;
+        w.x = pack_h2(e[8 * c], e[8 * c + 1]); w.y = pack_h2(e[8 * c + 2], e[8 * c + 3]);
+        w.z = pack_h2(e[8 * c + 4], e[8 * c + 5]); w.w = pack_h2(e[8 * c + 6], e[8 * c + 7]);
+        *reinterpret_cast<uint4 *>(tile + (size_t)c * (kTileRows * 16) + (size_t)r * 16) = w;
+    }
+}
+
+// 3-way fp16 split of a non-negative fp32 value below 65504 * (1 + 2^-11 + 2^-22)
+__device__ __forceinline__ void split3(float v, __half &a, __half &b, __half &c)
+{
+    a = __float2half_rn(v);
+    const float r1 = __fsub_rn(v, __half2float(a));
+    b = __float2half_rn(r1);
+    c = __float2half_rn(__fsub_rn(r1, __half2float(b)));
+}
+
+// ---- TMEM -> registers, 32 columns of this thread's lane ----
+__device__ __forceinline__ void tmem_ld32(uint32_t taddr, uint32_t (&r)[32])
+{
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+        "{%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,%28,%29,%30,%31}, [%32];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]),
+          "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]),
+          "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31])
+        : "r"(taddr)
+        : "memory");
+}
+// the registers of both loads are undefined until tcgen05.wait::ld; naming them as read-write operands keeps every use below
+__device__ __forceinline__ void tmem_ld_wait2(uint32_t (&a)[32], uint32_t (&b)[32])
+{
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 32; ++i) asm volatile("" : "+r"(a[i]), "+r"(b[i]));
+}
+
+__device__ __forceinline__ float fmin3(float a, float b, float c) { return fminf(fminf(a, b), c); }
+
+// minimum of 32 values with 3-input minima (16 instructions)
+__device__ __forceinline__ float min32(const uint32_t (&v)[32])
+{
+    float t[11];
+#pragma unroll
+    for (int i = 0; i < 10; ++i) t[i] = fmin3(__uint_as_float(v[3 * i]), __uint_as_float(v[3 * i + 1]), __uint_as_float(v[3 * i + 2]));
+    t[10] = fminf(__uint_as_float(v[30]), __uint_as_float(v[31]));
+    const float a = fmin3(t[0], t[1], t[2]), b = fmin3(t[3], t[4], t[5]), c = fmin3(t[6], t[7], t[8]), d = fminf(t[9], t[10]);
+    return fminf(fmin3(a, b, c), d);
+}
+
+// Running state of one thread's scan of its vector's scores: the smallest value and the runner-up are found
+// WITHOUT carrying indices through the 1000+ comparisons.  Every column belongs to one "group" (32 consecutive
+// columns, one tcgen05.ld) and one "class" (its position inside the group); two columns never share both.  The scan
+// keeps the two smallest group minima (with the group of the smallest) and the minimum of every class.  The smallest
+// score is the smallest group minimum; its column is (that group, the class holding the same value); the runner-up
+// is  min(second smallest group minimum, second smallest class minimum):  the true runner-up sits in another
+// group or -- if it shares the winner's group -- in another class, and both candidates are lower bounds of nothing
+// smaller than it.  About one min instruction per score instead of four with packed indices.
+struct Scan {
+    float a1, a2;       // two smallest group minima
+    int ga;             // group of a1
+    float cls[32];      // class minima
+    __device__ __forceinline__ void reset()
+    {
+        a1 = a2 = __int_as_float(0x7f800000);
+        ga = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cls[j] = __int_as_float(0x7f800000);
+    }
+    __device__ __forceinline__ void group(float g, int gid)
+    {
+        a2 = fminf(a2, fmaxf(a1, g));
+        ga = g < a1 ? gid : ga;
+        a1 = fminf(a1, g);
+    }
+    // two groups of 32 columns (ids gid, gid + 1)
+    __device__ __forceinline__ void feed(const uint32_t (&v0)[32], const uint32_t (&v1)[32], int gid)
+    {
+        group(min32(v0), gid);
+        group(min32(v1), gid + 1);
+#pragma unroll
+        for (int j = 0; j < 32; ++j) cls[j] = fmin3(cls[j], __uint_as_float(v0[j]), __uint_as_float(v1[j]));
+    }
+    // smallest score, runner-up, class of the smallest
+    __device__ __forceinline__ void finish(float &best, float &second, int &jbest) const
+    {
+        float b1 = __int_as_float(0x7f800000), b2 = b1;
+        int jb = 0;
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            b2 = fminf(b2, fmaxf(b1, cls[j]));
+            jb = cls[j] < b1 ? j : jb;
+            b1 = fminf(b1, cls[j]);
+        }
+        best = a1;                       // == b1
+        second = fminf(a2, b2);
+        jbest = jb;
+    }
+};
+
+}  // namespace tc
+}  // namespace fpc

@@ -189,6 +189,8 @@ def test_encode_host_matches_device_path(torch_cuda, model, synth, cbdir, B, L, 
         torch.cuda.synchronize()
         for k in ("c_in", "r", "r_qtz", "r_under", "ind1", "ind2", "idx"):
             assert np.array_equal(host[k].numpy(), ref[k]), "encode_host differs in %s (qtz=%s, chunks=%d)" % (k, qtz, chunks)
+        # the 7th element of the reference's tuple: cb_tot, counted on the device and downloaded with the rest
+        assert hist_equal(model.host_cb_tot(host), ref["cb_tot"]), "encode_host cb_tot differs (qtz=%s)" % qtz
     # second call reuses the workspace and the pipeline streams: still identical
     again = model.encode_host(cfg, fh, 0.25, 2.1, chunks=chunks)
     torch.cuda.synchronize()

@@ -30,6 +30,8 @@
 // of additions therefore differs and centroids agree with the reference to ~1e-15 relative
 // (tests state 1e-12).  With several ranks the caller all-reduces sums and counts (NCCL)
 // between fpc_kmeans_assign_accumulate and fpc_kmeans_finalize.
+#include <stdlib.h>
+
 #include "fpc_common.cuh"
 #include "fpc_vq.cuh"
 
@@ -282,8 +284,8 @@ __global__ void kmeans_fold_kernel(const double *__restrict__ ws_sums, const dou
 }
 
 // codebook = sums / (counts + 1e-20); statistics of cb_func.py:92-97
-__global__ void kmeans_finalize_kernel(const double *__restrict__ sums, const double *__restrict__ counts, int K,
-                                       double n_total, double *__restrict__ cb_out, double *__restrict__ stats)
+__global__ void kmeans_finalize_kernel(double *__restrict__ sums, double *__restrict__ counts, int K,
+                                       double n_total, double *__restrict__ cb_out, double *__restrict__ stats, int reset)
 {
     __shared__ double s_min[32], s_max[32], s_empty[32], s_w2[32];
     __shared__ double s_n;
@@ -309,6 +311,11 @@ __global__ void kmeans_finalize_kernel(const double *__restrict__ sums, const do
         const double den = c + 1e-20;
 #pragma unroll
         for (int d = 0; d < kDim; ++d) cb_out[(size_t)k * kDim + d] = sums[(size_t)k * kDim + d] / den;
+        if (reset) {            // leave the accumulator zeroed for the next iteration (no separate memset launches)
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) sums[(size_t)k * kDim + d] = 0.0;
+            counts[k] = 0.0;
+        }
         mn = fmin(mn, c); mx = fmax(mx, c);
         if (c == 0.0) em += 1.0;
         const double f = c / n_total;
@@ -352,6 +359,21 @@ __global__ void kmeans_gather_kernel(const double *__restrict__ cb, int K, const
 }
 
 int num_sms();
+// tensor-core screen (fpc_kmeans_tc.cu)
+int run_kmeans_assign_tc(const float *d_data, long N, const double *d_cb, int K, double *acc_sums, double *acc_counts,
+                         int32_t *d_idx, int R, void *d_pack, cudaStream_t st);
+size_t kmeans_tc_pack_bytes(int K);
+constexpr int kTcMinK = 128;      // below this the codebook is a fraction of one MMA tile: the CUDA-core kernel is as fast
+
+static bool tc_enabled()
+{
+    static int cached = -1;
+    if (cached < 0) {
+        const char *e = getenv("FPC_KMEANS_TC");        // A/B switch for measurements: FPC_KMEANS_TC=0 -> CUDA-core screen
+        cached = (e && e[0] == '0') ? 0 : 1;
+    }
+    return cached != 0;
+}
 
 }  // namespace fpc
 
@@ -359,15 +381,32 @@ using namespace fpc;
 
 extern "C" {
 
-// replicas of the (K,17)+(K) accumulation table: R K >= 512 rows, none from 512 entries up
-static int kmeans_replicas(int K) { return K >= 512 ? 1 : (512 + K - 1) / K; }
+// replicas of the (K,17)+(K) accumulation table: R K >= 2048 rows, none from that many entries up (the float64
+// atomics of 50 M vectors on fewer rows serialise in the L2)
+static int repl_rows()
+{
+    static int cached = 0;
+    if (cached == 0) {
+        const char *e = getenv("FPC_KMEANS_REPL_ROWS");     // measurement switch
+        cached = e ? atoi(e) : 2048;     // measured on 50 M vectors: K = 512 16.2 -> 11.5 ms, K = 256 14.1 -> 9.7 ms against 512 rows
+        if (cached < 1) cached = 2048;
+    }
+    return cached;
+}
+static int kmeans_replicas(int K) { const int rows = repl_rows(); return K >= rows ? 1 : (rows + K - 1) / K; }
+
+static size_t replica_bytes(int K)
+{
+    const int R = kmeans_replicas(K);
+    return R > 1 ? (((size_t)R * K * (kDim + 1) * sizeof(double) + 255) & ~(size_t)255) : 0;
+}
 
 size_t fpc_kmeans_workspace_bytes(long N, int K)
 {
     (void)N;
     if (K < 1) return 0;
-    const int R = kmeans_replicas(K);
-    return R > 1 ? (size_t)R * K * (kDim + 1) * sizeof(double) : 0;
+    // replicated accumulation tables of small codebooks + the packed operand image of the tensor-core screen
+    return replica_bytes(K) + (K >= kTcMinK ? kmeans_tc_pack_bytes(K) : 0);
 }
 
 int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
@@ -390,16 +429,24 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;
     // with a workspace and a small codebook the sums go to replicated tables first (see the kernel)
+    const bool have_ws = d_workspace && workspace_bytes >= fpc_kmeans_workspace_bytes(N, K);
     int R = d_sums ? kmeans_replicas(K) : 1;
-    if (R > 1 && (!d_workspace || workspace_bytes < fpc_kmeans_workspace_bytes(N, K))) R = 1;
+    if (R > 1 && !have_ws) R = 1;
     double *acc_sums = d_sums, *acc_counts = d_counts;
     if (R > 1) {
         acc_sums = (double *)d_workspace;
         acc_counts = acc_sums + (size_t)R * K * kDim;
         FPC_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, (size_t)R * K * (kDim + 1) * sizeof(double), st));
     }
-    kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
-    FPC_LAUNCH_CHECK();
+    if (K >= kTcMinK && have_ws && tc_enabled() && (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) {
+        // distance screen on the tensor cores (fpc_kmeans_tc.cu); same decisions, same accumulation
+        const int rc = run_kmeans_assign_tc(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R,
+                                            (char *)d_workspace + replica_bytes(K), st);
+        if (rc != FPC_OK) return rc;
+    } else {
+        kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
+        FPC_LAUNCH_CHECK();
+    }
     if (R > 1) {
         kmeans_fold_kernel<<<(K * (kDim + 1) + 255) / 256, 256, 0, st>>>(acc_sums, acc_counts, R, K, d_sums, d_counts);
         FPC_LAUNCH_CHECK();
@@ -411,7 +458,18 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
                         double *d_stats, void *stream)
 {
     if (!d_sums || !d_counts || !d_cb_out || K < 1) return FPC_ERR_ARG;
-    kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_sums, d_counts, K, n_total, d_cb_out, d_stats);
+    kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(const_cast<double *>(d_sums), const_cast<double *>(d_counts), K, n_total,
+                                                                 d_cb_out, d_stats, 0);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+/* fpc_kmeans_finalize on ONE accumulator  d_acc = [sums (K,17) | counts (K)]  (the layout a single all-reduce message
+ * wants), which is left zeroed for the next Lloyd iteration. */
+int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_out, double *d_stats, void *stream)
+{
+    if (!d_acc || !d_cb_out || K < 1) return FPC_ERR_ARG;
+    kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_acc, d_acc + (size_t)K * kDim, K, n_total, d_cb_out, d_stats, 1);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -8,13 +8,14 @@
 // vector (one min instruction per score) and decide the vectors whose runner-up is more than the slack away; the
 // few others are re-done by a warp with the fp32 screen + float64 evaluation the CUDA-core kernel uses.
 //
-// One CTA per SM, 13 warps:
+// One CTA per SM, 12 warps:
 //   warps 0..7   scan.  Warp w reads TMEM lanes 32 (w % 4) .. +31 (one vector per lane) and the column half w / 4
 //                of every 128-centroid chunk; then merge, decision, fallback, float64 atomics for the sums.
-//   warps 8..11  load.  Thread r converts vector r of the next 128-vector tile into the fp16-pair A operand row
-//                (scaled by -2 beta) in a 4-deep ring of 16 KB tiles.
-//   warp 12      lane 0 issues the MMAs: per tile and 128-centroid chunk four K = 16 slabs into one of four
-//                128-column TMEM slots; tcgen05.commit releases the A tile and publishes the slot.
+//   warps 8..10  load.  Thread r converts vectors r (and r + 96) of the next 128-vector tile (brought on chip by one
+//                bulk copy) into fp16-pair A operand rows (scaled by -2 beta) in a ring of 16 KB tiles.
+//   warp 11      lane 0 issues the MMAs: per tile and 128-centroid chunk four K = 16 slabs into one of four
+//                128-column TMEM slots; tcgen05.commit releases the A tile and publishes the slot.  Lane 1 issues
+//                the bulk copies of the raw tiles.
 // The B operand (the whole codebook, <= 1024 x 128 B) is resident in shared memory: one bulk copy per launch from
 // the image kmeans_tc_pack_kernel writes (also: the fp32 shadow and the scale).
 #include "fpc_common.cuh"
@@ -23,15 +24,23 @@
 
 namespace fpc {
 
-constexpr int kTcScan = 256, kTcLoad = 128, kTcThreads = kTcScan + kTcLoad + 32;
-constexpr int kTcASlots = 4, kTcDSlots = 4;
+// Scanner warps: 8 (two per scheduler).  The scan is bound by the min-instruction rate of the ALU pipe, not by latency:
+// 16 warps (measured) were 25 % slower -- same scan time, twice the merge / decision overhead and register spills.
+constexpr int kTcScanWarps = 8;
+constexpr int kTcColParts = kTcScanWarps / 4;                  // column parts of a 128-centroid chunk (one per warp of a lane quarter)
+constexpr int kTcLdPerUnit = 128 / (32 * kTcColParts);         // 32-column TMEM loads per thread and chunk
+constexpr int kTcScan = 32 * kTcScanWarps, kTcLoad = 96, kTcThreads = kTcScan + kTcLoad + 32;   // a multiple of 128 threads
+constexpr int kTcASlots = 2, kTcDSlots = 4, kTcRawSlots = 4;
+constexpr int kTcRawFloats = 128 * kDim;           // one tile of the data set: 8704 contiguous bytes
 constexpr int kTcShadowLd = 20;                    // fp32 shadow row: c0..c16, -, ||c||^2, -
-// slack of a TC decision: 2^-15 (||x|| + Cmax)^2 = 512 u R (fpc_tc.cuh: the operand format costs <= 10 u R per score,
-// the accumulation is measured; a comparison involves two scores)
-constexpr float kTcSlackRel = 3.0517578125e-5f;
-constexpr float kF32SlackRel = 7.62939453125e-6f; // 128 u R: the fp32 screen of the fallback (fpc_kmeans.cu)
+// Slack of a decision, both screens: 2^-17 (||x|| + Cmax)^2 = 128 u R.  A comparison involves two scores: the
+// tensor-core scores are within 10 u R (operand format, fpc_tc.cuh) plus the accumulation error, measured at <= 3 u R
+// in total over the scales of tests/test_gpu_quant_kmeans.py::test_tc_screen_score_error_budget (asserted <= 64 u R);
+// the fp32 screen of the fallback is within 25 u R (21 u R as in fpc_kmeans.cu + the 22-bit shadow it reads here).
+constexpr float kTcSlackRel = 7.62939453125e-6f;
+constexpr float kF32SlackRel = 7.62939453125e-6f;
 
-struct KmeansTcMeta { float beta, cmax; int K, Kp; };
+struct KmeansTcMeta { float beta, cmax; int K, Kp; unsigned int n_fallback, n_rows; unsigned long long prof[8]; };
 __host__ __device__ constexpr size_t tc_image_bytes(int Kp) { return (size_t)Kp * tc::kK * 2; }
 __host__ __device__ constexpr size_t tc_pack_bytes(int K)
 {
@@ -70,7 +79,7 @@ kmeans_tc_pack_kernel(const double *__restrict__ cb, int K, unsigned char *__res
     amax = 0.0f; n2max = 0.0f;
     for (int w = 0; w < (int)(blockDim.x >> 5); ++w) { amax = fmaxf(amax, s_red[w]); n2max = fmaxf(n2max, s_red2[w]); }
     const float beta = tc::scale_for(amax);
-    if (threadIdx.x == 0) { meta->beta = beta; meta->cmax = __fsqrt_ru(n2max); meta->K = K; meta->Kp = Kp; }
+    if (threadIdx.x == 0) { meta->beta = beta; meta->cmax = __fsqrt_ru(n2max); meta->K = K; meta->Kp = Kp; meta->n_fallback = 0; meta->n_rows = 0; for (int i = 0; i < 8; ++i) meta->prof[i] = 0; }
     for (int k = threadIdx.x; k < Kp; k += blockDim.x) {
         unsigned char *tile = image + (size_t)(k >> 7) * tc::kTileBytes;
         float xs[kDim];
@@ -106,9 +115,61 @@ __device__ __forceinline__ float tc_screen17(const float (&x)[kDim], const float
     return s;
 }
 
-struct TcSmem {
-    static constexpr int offA = 0;                                    // after the B image (dynamic offset)
-};
+// One undecided vector, by a whole warp: fp32 screen of this lane's centroids k = lane + 32 j from the RESIDENT operand
+// image (hi + lo of an fp16 pair is exact in fp32, so the image doubles as a 22-bit shadow of beta c; the norm is
+// n0 + n1 + n2), then float64 direct-form distances of the candidates inside the fp32 slack, ascending k with strict <
+// (numpy's first minimum, cb_func.py:66).  Everything in the scale of the operands (x beta^2), which the bounds do not see.
+__device__ __noinline__ int tc_exact_assign(const float *__restrict__ xrow, float rr2, float beta, int K,
+                                            const unsigned char *__restrict__ sB, const double *__restrict__ cb, int lane)
+{
+    const float inf = __int_as_float(0x7f800000);
+    float xu[kDim], xs[kDim];
+#pragma unroll
+    for (int d = 0; d < kDim; ++d) { xu[d] = __ldg(xrow + d); xs[d] = -2.0f * beta * xu[d]; }
+    const float slack32 = __fmul_ru(__fadd_ru(__fmul_ru(rr2, kF32SlackRel), 1e-30f), beta * beta);
+    float sv[32];
+    float m = inf;
+#pragma unroll
+    for (int j = 0; j < 32; ++j) {
+        const int k = lane + 32 * j;
+        sv[j] = inf;
+        if (k < K) {
+            const unsigned char *rowp = sB + (size_t)(k >> 7) * tc::kTileBytes + (size_t)(k & 127) * 16;
+            uint32_t wds[28];
+#pragma unroll
+            for (int c8 = 0; c8 < 7; ++c8) {
+                const uint4 t4 = *reinterpret_cast<const uint4 *>(rowp + (size_t)c8 * 2048);
+                wds[4 * c8] = t4.x; wds[4 * c8 + 1] = t4.y; wds[4 * c8 + 2] = t4.z; wds[4 * c8 + 3] = t4.w;
+            }
+            auto h = [&](int e) { return __half2float(__ushort_as_half((unsigned short)(wds[e >> 1] >> ((e & 1) * 16)))); };
+            float sacc = __fadd_rn(__fadd_rn(h(51), h(52)), h(53));
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) sacc = __fmaf_rn(xs[d], __fadd_rn(h(3 * d), h(3 * d + 1)), sacc);
+            sv[j] = sacc;
+            m = fminf(m, sacc);
+        }
+    }
+    for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
+    const float thr = __fadd_ru(m, slack32);
+    double bd = Rn<double>::inf();
+    int bk = 0x7fffffff;
+#pragma unroll 1
+    for (int j = 0; j < 32; ++j) {
+        float sj = inf;
+#pragma unroll
+        for (int t = 0; t < 32; ++t) sj = t == j ? sv[t] : sj;
+        if (sj <= thr) {
+            const int k = lane + 32 * j;
+            double xd[kDim], cd[kDim];
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) { xd[d] = (double)xu[d]; cd[d] = cb[(size_t)k * kDim + d]; }
+            const double dd = dist17<double>(xd, cd);
+            if (dd < bd || bk == 0x7fffffff) { bd = dd; bk = k; }      // ascending k per lane: first minimum kept
+        }
+    }
+    warp_argmin(bd, bk);
+    return bk == 0x7fffffff ? 0 : bk;     // NaN input: no candidate; numpy's argmin of all-NaN distances is 0
+}
 
 __global__ void __launch_bounds__(kTcThreads, 1)
 kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__restrict__ cb, int K,
@@ -121,12 +182,13 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
     const int nchunks = Kp >> 7;
     unsigned char *sB = smem;
     unsigned char *sA = smem + tc_image_bytes(Kp);
-    float *pm = reinterpret_cast<float *>(sA + kTcASlots * tc::kTileBytes);        // [128][4]: best, second, column (hh = 1 half)
-    int *dec = reinterpret_cast<int *>(pm + 128 * 4);                               // [128] decided centroid (or -1)
+    float *raw = reinterpret_cast<float *>(sA + kTcASlots * tc::kTileBytes);       // [kTcRawSlots][128][17] fp32, as in HBM
+    float *pm = raw + kTcRawSlots * kTcRawFloats;                                   // [3][128][4]: best, second, column of column quarters 1..3
+    int *dec = reinterpret_cast<int *>(pm + 3 * 128 * 4);                               // [128] decided centroid (or -1)
     uint64_t *bars = reinterpret_cast<uint64_t *>(dec + 128);
     uint64_t *b_full = bars, *a_full = bars + 1, *a_empty = a_full + kTcASlots, *d_full = a_empty + kTcASlots,
-             *d_empty = d_full + kTcDSlots;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(d_empty + kTcDSlots);
+             *d_empty = d_full + kTcDSlots, *raw_full = d_empty + kTcDSlots, *raw_empty = raw_full + kTcRawSlots;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kTcRawSlots);
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const long my_tiles = ntiles > (long)blockIdx.x ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -135,6 +197,7 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
         mbar_init(b_full, 1);
         for (int s = 0; s < kTcASlots; ++s) { mbar_init(&a_full[s], kTcLoad / 32); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < kTcDSlots; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kTcScan / 32); }
+        for (int s = 0; s < kTcRawSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], (kTcScan + kTcLoad) / 32); }
         mbar_fence_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -143,10 +206,16 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
     umma::fence_after_sync();
     const uint32_t tb = *tmem_slot;
     const float beta = meta->beta, cmax = meta->cmax;
+    // a tile of 128 vectors is 8704 contiguous bytes of the data set: one bulk copy brings it on chip, where the loaders
+    // (operand conversion) and the scanners (norms, sums) read their rows -- a per-thread row load from global memory
+    // is a 68-byte-strided access that costs the L1 seventeen wavefronts per instruction.  The last, partial tile of
+    // the data set is read from global memory instead (its size need not be a multiple of 16 bytes).
+    auto tile_index = [&](long i) { return (long)blockIdx.x + i * gridDim.x; };
+    auto tile_is_bulk = [&](long t) { return (t + 1) * 128 <= N; };
 
     if (warp == kTcThreads / 32 - 1) {
-        // ---------------- MMA issuer (+ the one bulk copy of the codebook image) ----------------
         if (lane == 0) {
+            // ---------------- MMA issuer (+ the one bulk copy of the codebook image) ----------------
             const uint32_t bytes = (uint32_t)tc_image_bytes(Kp);
             mbar_arrive_expect_tx(b_full, bytes);
             for (uint32_t off = 0; off < bytes; off += tc::kTileBytes)
@@ -172,137 +241,186 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
                 }
                 umma::commit(&a_empty[sa]);
             }
+        } else if (lane == 1) {
+            // ---------------- raw-tile producer: HBM -> shared memory, kTcRawSlots tiles ahead ----------------
+            for (long i = 0; i < my_tiles; ++i) {
+                const int sr = (int)(i % kTcRawSlots);
+                const uint32_t nr = (uint32_t)(i / kTcRawSlots);
+                if (nr > 0) mbar_wait(&raw_empty[sr], (nr - 1) & 1u);
+                const long t = tile_index(i);
+                if (tile_is_bulk(t)) {
+                    mbar_arrive_expect_tx(&raw_full[sr], kTcRawFloats * 4);
+                    bulk_g2s(raw + sr * kTcRawFloats, data + t * kTcRawFloats, kTcRawFloats * 4, &raw_full[sr]);
+                } else {
+                    mbar_arrive(&raw_full[sr]);
+                }
+            }
         }
     } else if (warp >= kTcScan / 32) {
         // ---------------- loaders: vectors -> fp16-pair A tiles ----------------
-        const int r = tid - kTcScan;
+        const int r0 = tid - kTcScan;
         const __half one = __float2half_rn(1.0f);
         for (long i = 0; i < my_tiles; ++i) {
-            const int sa = (int)(i % kTcASlots);
+            const int sa = (int)(i % kTcASlots), sr = (int)(i % kTcRawSlots);
             const uint32_t na = (uint32_t)(i / kTcASlots);
-            const long row = ((long)blockIdx.x + i * gridDim.x) * 128 + r;
-            float xs[kDim];
-#pragma unroll
-            for (int d = 0; d < kDim; ++d) xs[d] = row < N ? __ldg(data + row * kDim + d) : 0.0f;
-#pragma unroll
-            for (int d = 0; d < kDim; ++d) {
-                float v = -2.0f * beta * xs[d];                       // exact (powers of two)
-                if (!(fabsf(v) <= tc::kMaxScaledX)) v = 0.0f;         // out of range (or NaN): the scan side sends the row to the exact path
-                xs[d] = v;
-            }
+            const long t = tile_index(i);
+            mbar_wait(&raw_full[sr], (uint32_t)(i / kTcRawSlots) & 1u);
             if (na > 0) mbar_wait(&a_empty[sa], (na - 1) & 1u);
-            tc::store_row<true>(sA + sa * tc::kTileBytes, r, xs, one, one, one);
+#pragma unroll 1
+            for (int r = r0; r < 128; r += kTcLoad) {
+                float xs[kDim];
+                if (tile_is_bulk(t)) {
+#pragma unroll
+                    for (int d = 0; d < kDim; ++d) xs[d] = raw[sr * kTcRawFloats + r * kDim + d];
+                } else {
+                    const long row = t * 128 + r;
+#pragma unroll
+                    for (int d = 0; d < kDim; ++d) xs[d] = row < N ? __ldg(data + row * kDim + d) : 0.0f;
+                }
+#pragma unroll
+                for (int d = 0; d < kDim; ++d) {
+                    float v = -2.0f * beta * xs[d];                       // exact (powers of two)
+                    if (!(fabsf(v) <= tc::kMaxScaledX)) v = 0.0f;         // out of range (or NaN): the scan side sends the row to the exact path
+                    xs[d] = v;
+                }
+                tc::store_row<true>(sA + sa * tc::kTileBytes, r, xs, one, one, one);
+            }
             umma::fence_async_smem();
             __syncwarp();
-            if (lane == 0) mbar_arrive(&a_full[sa]);
+            if (lane == 0) { mbar_arrive(&raw_empty[sr]); mbar_arrive(&a_full[sa]); }
         }
     } else {
         // ---------------- scanners ----------------
-        const int q = warp & 3, hh = warp >> 2;
+        const int q = warp & 3, cq = warp >> 2;
         const int r = 32 * q + lane;
-        const float inf = __int_as_float(0x7f800000);
-        const float *shadow = reinterpret_cast<const float *>(packed + 256 + tc_image_bytes(Kp));
         uint32_t u = 0;
+#ifdef FPC_KMEANS_TC_PROF
+        long long pf[8] = {0, 0, 0, 0, 0, 0, 0, 0}, pt = clock64();
+#define TCP(i) do { const long long t_ = clock64(); pf[i] += t_ - pt; pt = t_; } while (0)
+#else
+#define TCP(i) do { } while (0)
+#endif
         for (long i = 0; i < my_tiles; ++i) {
-            const long row = ((long)blockIdx.x + i * gridDim.x) * 128 + r;
+            const long t = tile_index(i);
+            const long row = t * 128 + r;
             const bool valid = row < N;
-            float x[kDim];
-#pragma unroll
-            for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + row * kDim + d) : 0.0f;
+            const int sr = (int)(i % kTcRawSlots);
             tc::Scan sc;
             sc.reset();
             for (int c = 0; c < nchunks; ++c, ++u) {
                 const int ds = (int)(u % kTcDSlots);
+                TCP(0);
                 mbar_wait(&d_full[ds], (u / kTcDSlots) & 1u);
+                TCP(1);
                 umma::fence_after_sync();
-                uint32_t v0[32], v1[32];
-                const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 128 + 64 * hh);
-                tc::tmem_ld32(ta, v0);
-                tc::tmem_ld32(ta + 32, v1);
-                tc::tmem_ld_wait2(v0, v1);
-                umma::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&d_empty[ds]);
-                sc.feed(v0, v1, 2 * c);
+                const uint32_t ta = tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 128 + 32 * kTcLdPerUnit * cq);
+                if (kTcLdPerUnit == 1) {
+                    uint32_t v[32];
+                    tc::tmem_ld32(ta, v);
+                    tc::tmem_ld_wait(v);
+                    umma::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[ds]);
+                    sc.feed(v, 2 * c);
+                } else {
+                    uint32_t v0[32], v1[32];
+                    tc::tmem_ld32(ta, v0);
+                    tc::tmem_ld32(ta + 32, v1);
+                    tc::tmem_ld_wait(v0);
+                    tc::tmem_ld_wait(v1);
+                    umma::fence_before_sync();
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&d_empty[ds]);
+                    sc.feed(v0, 4 * c);
+                    sc.feed(v1, 4 * c + 2);
+                }
             }
+            TCP(0);
             float best, second;
             int jb;
             sc.finish(best, second, jb);
-            int col = 128 * (sc.ga >> 1) + 64 * hh + 32 * (sc.ga & 1) + jb;
-            if (hh == 1) { pm[r * 4] = best; pm[r * 4 + 1] = second; pm[r * 4 + 2] = __int_as_float(col); }
-            named_bar_sync(1, kTcScan);
-            if (hh == 0) {
-                const float ob = pm[r * 4], os = pm[r * 4 + 1];
-                const int oc = __float_as_int(pm[r * 4 + 2]);
-                second = fminf(fminf(second, os), fmaxf(best, ob));
-                if (ob < best) { best = ob; col = oc; }
-                // per-vector constants of the decision
-                float nx = 0.0f, amax = 0.0f;
+            // group id -> first column: 2 (or 4) groups of 16 per chunk and column part
+            int col = kTcLdPerUnit == 1 ? 128 * (sc.ga >> 1) + 32 * cq + 16 * (sc.ga & 1) + jb
+                                        : 128 * (sc.ga >> 2) + 64 * cq + 16 * (sc.ga & 3) + jb;
+            if (cq > 0) { float *p = pm + ((cq - 1) * 128 + r) * 4; p[0] = best; p[1] = second; p[2] = __int_as_float(col); }
+            // this thread's vector (the raw tile has long arrived: the MMAs above consumed its conversion)
+            float x[kDim];
+            mbar_wait(&raw_full[sr], (uint32_t)(i / kTcRawSlots) & 1u);
+            if (tile_is_bulk(t)) {
 #pragma unroll
-                for (int d = 0; d < kDim; ++d) { nx = __fmaf_ru(x[d], x[d], nx); amax = fmaxf(amax, fabsf(x[d])); }
-                const float rr = __fadd_ru(__fsqrt_ru(nx), cmax);
-                const float rr2 = __fmul_ru(rr, rr);
+                for (int d = 0; d < kDim; ++d) x[d] = raw[sr * kTcRawFloats + r * kDim + d];
+            } else {
+#pragma unroll
+                for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + row * kDim + d) : 0.0f;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(&raw_empty[sr]);
+            TCP(2);
+            named_bar_sync(1, kTcScan);
+            TCP(3);
+            if (cq == 0) {
+#pragma unroll
+                for (int o = 0; o < kTcColParts - 1; ++o) {
+                    const float *p = pm + (o * 128 + r) * 4;
+                    const float ob = p[0], os = p[1];
+                    const int oc = __float_as_int(p[2]);
+                    second = fminf(fminf(second, os), fmaxf(best, ob));
+                    if (ob < best) { best = ob; col = oc; }
+                }
+                // per-vector constants of the decision: R = (||x|| + Cmax)^2 <= 2 (||x||^2 + Cmax^2), rounded up
+                float nx = 0.0f;
+#pragma unroll
+                for (int d = 0; d < kDim; ++d) nx = __fmaf_ru(x[d], x[d], nx);
+                const float rr2 = __fmul_ru(2.0f, __fadd_ru(nx, __fmul_ru(cmax, cmax)));
                 const float slack_tc = __fmul_ru(__fmul_ru(rr2, kTcSlackRel), beta * beta);   // scores are scaled by beta^2
-                const bool in_range = 2.0f * beta * amax <= tc::kMaxScaledX;                   // NaN -> false
+                // every |(-2 beta x)_d| <= 2 beta ||x||: inside the operand range if 4 beta^2 ||x||^2 <= 1024^2 (NaN -> false)
+                const bool in_range = __fmul_ru(4.0f * beta * beta, nx) <= tc::kMaxScaledX * tc::kMaxScaledX;
                 bool decided = in_range && col < K && (second > __fadd_ru(best, slack_tc));
                 int b = decided ? col : -1;
-                // the undecided vectors (near-ties, duplicate centroids, out-of-range rows): one at a time by the whole
-                // warp -- fp32 screen of all K centroids (32 per lane), then float64 direct-form distances of the
-                // candidates inside the fp32 slack, ascending k with strict < (numpy's first minimum)
+                // the undecided vectors (near-ties, duplicate centroids, out-of-range rows): one at a time by the whole warp
                 unsigned todo = __ballot_sync(0xffffffffu, valid && !decided);
+                if (todo && lane == 0) atomicAdd(const_cast<unsigned int *>(&meta->n_fallback), (unsigned)__popc(todo));
                 while (todo) {
                     const int src = __ffs(todo) - 1;
                     todo &= todo - 1;
-                    float xs[kDim];
-#pragma unroll
-                    for (int d = 0; d < kDim; ++d) xs[d] = __shfl_sync(0xffffffffu, x[d], src);
-                    const float slack32 = __fadd_ru(__fmul_ru(__shfl_sync(0xffffffffu, rr2, src), kF32SlackRel), 1e-30f);
-                    float m = inf;
-                    for (int k = lane; k < K; k += 32) m = fminf(m, tc_screen17(xs, shadow + (size_t)k * kTcShadowLd));
-                    for (int off = 16; off > 0; off >>= 1) m = fminf(m, __shfl_xor_sync(0xffffffffu, m, off));
-                    const float thr = __fadd_ru(m, slack32);
-                    double bd = Rn<double>::inf();
-                    int bk = 0x7fffffff;
-                    for (int k = lane; k < K; k += 32) {
-                        if (tc_screen17(xs, shadow + (size_t)k * kTcShadowLd) <= thr) {
-                            double xd[kDim], cd[kDim];
-#pragma unroll
-                            for (int d = 0; d < kDim; ++d) { xd[d] = (double)xs[d]; cd[d] = cb[(size_t)k * kDim + d]; }
-                            const double dd = dist17<double>(xd, cd);
-                            if (dd < bd || bk == 0x7fffffff) { bd = dd; bk = k; }     // ascending k per lane: first minimum kept
-                        }
-                    }
-                    warp_argmin(bd, bk);
-                    if (bk == 0x7fffffff) bk = 0;         // NaN input: numpy's argmin returns the first NaN; index 0 here
+                    const int bk = tc_exact_assign(data + (row - lane + src) * kDim, __shfl_sync(0xffffffffu, rr2, src), beta, K, sB, cb, lane);
                     if (lane == src) b = bk;
                 }
                 dec[r] = valid ? b : -1;
                 if (valid && idx_out) idx_out[row] = b;
             }
+            TCP(4);
             named_bar_sync(1, kTcScan);
-            // sums and counts (cb_func.py:82-86): float64 atomics, the 17 dimensions split between the two warps of a row
+            TCP(5);
+            // sums and counts (cb_func.py:82-86): float64 atomics, the 17 dimensions split between the four warps of a row
             if (sums) {
                 const int b = dec[r];
                 if (b >= 0) {
                     double *s2 = sums;
                     double *c2 = counts;
                     if (R > 1) {
-                        const int rep = (int)(((long)blockIdx.x * kTcScan + tid) % R);
+                        const int rep = (int)(((long)blockIdx.x * 128 + r) % R);
                         s2 += (size_t)rep * K * kDim;
                         c2 += (size_t)rep * K;
                     }
                     s2 += (size_t)b * kDim;
-                    if (hh == 0) {
+                    // the 17 dimensions (+ the count) are split between the warps that share the row
+                    const int d0 = cq * 18 / kTcColParts, d1 = (cq + 1) * 18 / kTcColParts;
 #pragma unroll
-                        for (int d = 0; d < 9; ++d) atomicAdd(s2 + d, (double)x[d]);
-                    } else {
-#pragma unroll
-                        for (int d = 9; d < kDim; ++d) atomicAdd(s2 + d, (double)x[d]);
-                        atomicAdd(c2 + b, 1.0);
-                    }
+                    for (int d = 0; d < kDim; ++d)
+                        if (d >= d0 && d < d1) atomicAdd(s2 + d, (double)x[d]);
+                    if (d1 == 18) atomicAdd(c2 + b, 1.0);
                 }
             }
+            TCP(6);
         }
+#ifdef FPC_KMEANS_TC_PROF
+        if (tid == 0 && blockIdx.x == 0) {
+            for (int k2 = 0; k2 < 7; ++k2) const_cast<unsigned long long *>(meta->prof)[k2] = (unsigned long long)pf[k2];
+            const_cast<unsigned long long *>(meta->prof)[7] = (unsigned long long)my_tiles;
+        }
+#endif
+#undef TCP
     }
     umma::fence_before_sync();
     __syncthreads();
@@ -312,7 +430,8 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
 size_t kmeans_tc_smem_bytes(int K)
 {
     const int Kp = (K + 127) / 128 * 128;
-    return tc_image_bytes(Kp) + (size_t)kTcASlots * tc::kTileBytes + 128 * 4 * 4 + 128 * 4 + (1 + 2 * kTcASlots + 2 * kTcDSlots) * 8 + 16;
+    return tc_image_bytes(Kp) + (size_t)kTcASlots * tc::kTileBytes + (size_t)kTcRawSlots * kTcRawFloats * 4 + 3 * 128 * 4 * 4 + 128 * 4 +
+           (1 + 2 * kTcASlots + 2 * kTcDSlots + 2 * kTcRawSlots) * 8 + 16;
 }
 
 int num_sms();
@@ -328,6 +447,7 @@ int run_kmeans_assign_tc(const float *d_data, long N, const double *d_cb, int K,
     static bool configured[kMaxDevices] = {};
     { const int rc = ensure_dynamic_smem(kmeans_assign_tc_kernel, (int)kmeans_tc_smem_bytes(FPC_MAX_VQ_ENTRIES), configured);
       if (rc != FPC_OK) return rc; }
+    if ((reinterpret_cast<uintptr_t>(d_data) & 15) != 0) return FPC_ERR_ARG;      // bulk copies of whole tiles (torch allocations are 256-byte aligned)
     const long ntiles = (N + 127) / 128;
     const int grid = (int)(ntiles < sms ? ntiles : sms);
     kmeans_assign_tc_kernel<<<grid, kTcThreads, kmeans_tc_smem_bytes(K), st>>>(d_data, N, d_cb, K, (const unsigned char *)d_pack,
@@ -338,4 +458,83 @@ int run_kmeans_assign_tc(const float *d_data, long N, const double *d_cb, int K,
 
 size_t kmeans_tc_pack_bytes(int K) { return tc_pack_bytes(K); }
 
+// ------------------------------------------------------------------------------------------
+// selftest: the raw screened scores of up to 128 vectors against a codebook, un-scaled, so that a test can measure
+// the error of the tensor-core path against float64 (the accumulation term of the error budget in fpc_tc.cuh)
+// ------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(128, 1)
+tc_scores_selftest_kernel(const float *__restrict__ x, int n, int K, const unsigned char *__restrict__ packed, float *__restrict__ out)
+{
+    extern __shared__ __align__(1024) unsigned char smem[];
+    const KmeansTcMeta *meta = reinterpret_cast<const KmeansTcMeta *>(packed);
+    const int Kp = (K + 127) / 128 * 128, nchunks = Kp >> 7;
+    unsigned char *sB = smem, *sA = smem + tc_image_bytes(Kp);
+    __shared__ uint64_t bar[2];
+    __shared__ uint32_t tmem_base;
+    const int tid = threadIdx.x, warp = tid >> 5;
+    if (warp == 0) umma::tmem_alloc(&tmem_base, 128);
+    if (tid == 0) { mbar_init(&bar[0], 1); mbar_init(&bar[1], 1); mbar_fence_init(); }
+    const float beta = meta->beta;
+    {
+        float xs[kDim];
+#pragma unroll
+        for (int d = 0; d < kDim; ++d) xs[d] = tid < n ? -2.0f * beta * x[(size_t)tid * kDim + d] : 0.0f;
+        const __half one = __float2half_rn(1.0f);
+        tc::store_row<true>(sA, tid, xs, one, one, one);
+    }
+    umma::fence_async_smem();
+    umma::fence_before_sync();
+    __syncthreads();
+    umma::fence_after_sync();
+    const uint32_t tb = tmem_base;
+    if (tid == 0) {
+        const uint32_t bytes = (uint32_t)tc_image_bytes(Kp);
+        mbar_arrive_expect_tx(&bar[0], bytes);
+        for (uint32_t off = 0; off < bytes; off += tc::kTileBytes) bulk_g2s(sB + off, packed + 256 + off, tc::kTileBytes, &bar[0]);
+    }
+    mbar_wait(&bar[0], 0);
+    for (int c = 0; c < nchunks; ++c) {
+        if (tid == 0) {
+            const uint32_t idesc = tc::instr_desc_f16(128, 128);
+#pragma unroll
+            for (int ks = 0; ks < 4; ++ks)
+                tc::mma_f16(tb, umma::smem_desc(smem_u32(sA) + ks * tc::kSlabBytes, 128),
+                            umma::smem_desc(smem_u32(sB) + c * tc::kTileBytes + ks * tc::kSlabBytes, 128), idesc, ks > 0);
+            umma::commit(&bar[1]);
+        }
+        mbar_wait(&bar[1], c & 1);
+        umma::fence_after_sync();
+        for (int c0 = 0; c0 < 128; c0 += 32) {
+            uint32_t v[32];
+            tc::tmem_ld32(tb + ((uint32_t)(warp * 32) << 16) + c0, v);
+            tc::tmem_ld_wait(v);
+            if (tid < n)
+#pragma unroll
+                for (int j = 0; j < 32; ++j) out[(size_t)tid * Kp + c * 128 + c0 + j] = __uint_as_float(v[j]) / (beta * beta);
+        }
+        umma::fence_before_sync();
+        __syncthreads();
+        umma::fence_after_sync();
+    }
+    if (warp == 0) umma::tmem_dealloc(tb, 128);
+}
+
 }  // namespace fpc
+
+// scores[v][k] = ||c_k||^2 - 2 <x_v, c_k> as the tensor-core screen computes them (n <= 128 vectors, K <= 1024 centroids;
+// out: n x Kp floats, Kp = K rounded up to 128; d_pack: fpc_kmeans_workspace_bytes(n, K) bytes of scratch)
+extern "C" int fpc_selftest_tc_scores(const float *d_x, int n, const double *d_cb, int K, float *d_out, void *d_pack, void *stream)
+{
+    using namespace fpc;
+    if (!d_x || !d_cb || !d_out || !d_pack) return FPC_ERR_ARG;
+    if (n < 1 || n > 128 || K < 1 || K > FPC_MAX_VQ_ENTRIES) return FPC_ERR_SHAPE;
+    cudaStream_t st = (cudaStream_t)stream;
+    kmeans_tc_pack_kernel<<<1, 1024, 0, st>>>(d_cb, K, (unsigned char *)d_pack);
+    FPC_LAUNCH_CHECK();
+    const int Kp = (K + 127) / 128 * 128;
+    const size_t smem = tc_image_bytes(Kp) + tc::kTileBytes;
+    FPC_CUDA_TRY(cudaFuncSetAttribute(tc_scores_selftest_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    tc_scores_selftest_kernel<<<1, 128, smem, st>>>(d_x, n, K, (const unsigned char *)d_pack, d_out);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}

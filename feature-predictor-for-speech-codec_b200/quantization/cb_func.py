@@ -61,8 +61,8 @@ def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
     counts = torch.zeros((K,), dtype=torch.float64, device=dev) if want_sums else None
     idx = torch.empty((n,), dtype=torch.int32, device=dev) if want_idx else None
     with torch.cuda.device(dev):
-        # scratch for the replicated accumulation tables of small codebooks (0 bytes from 512 entries up)
-        need = N.lib().fpc_kmeans_workspace_bytes(n, K) if want_sums else 0
+        # scratch: replicated accumulation tables of small codebooks + the operand image of the tensor-core screen
+        need = N.lib().fpc_kmeans_workspace_bytes(n, K)
         ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
         N.check(N.lib().fpc_kmeans_assign_accumulate(
             data_dev.data_ptr(), n, cb_dev.data_ptr(), K,
@@ -72,21 +72,50 @@ def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
     return sums, counts, idx
 
 
+_acc_cache = {}     # (device, K) -> [accumulator, workspace]: zeroed once, re-zeroed by every finalize
+
+
+def _accumulator(dev, K, n):
+    torch = _torch()
+    hit = _acc_cache.get((str(dev), K))
+    need = N.lib().fpc_kmeans_workspace_bytes(n, K)
+    if hit is None or hit[1].numel() < need:
+        if len(_acc_cache) > 64:
+            _acc_cache.clear()
+        hit = [torch.zeros(K * 18, dtype=torch.float64, device=dev), torch.empty(max(need, 1), dtype=torch.uint8, device=dev)]
+        _acc_cache[(str(dev), K)] = hit
+    return hit
+
+
 def update_device(data_dev, cb_dev, group=None):
     """One Lloyd iteration entirely on the device (+ the all-reduce when distributed), no host synchronisation.
     Returns (new codebook (K,17) f64 device tensor, stats (5,) f64 device tensor = min count, max count, #empty,
-    sum (count/N)^2, N; the global vector count N as a 0-d device tensor view of stats[4])."""
+    sum (count/N)^2, N; the global vector count N as a 0-d device tensor view of stats[4]).
+
+    Per iteration: the assign kernel(s) accumulate into ONE buffer [sums (K,17) | counts (K)], the ranks all-reduce that
+    buffer in place (one message, no pack / unpack copies), and fpc_kmeans_finalize_acc divides and leaves the buffer
+    zeroed for the next iteration -- no memset and no allocation inside the loop."""
     torch = _torch()
     dev = data_dev.device
     K = cb_dev.shape[0]
-    sums, counts, _ = assign_accumulate(data_dev, cb_dev)
-    fpc_dist.allreduce_kmeans(sums, counts, data_dev.shape[0], group, want_total=False)
+    n = data_dev.shape[0]
+    cb_dev = cb_dev.contiguous()
+    acc, ws = _accumulator(dev, K, n)
     out = torch.empty((K, 17), dtype=torch.float64, device=dev)
     stats = torch.empty((5,), dtype=torch.float64, device=dev)
-    with torch.cuda.device(dev):
-        # n_total = 0: nb_vectors is the sum of the (all-reduced) counts, taken on the device
-        N.check(N.lib().fpc_kmeans_finalize(sums.data_ptr(), counts.data_ptr(), K, 0.0, out.data_ptr(),
-                                            stats.data_ptr(), N.current_stream(dev)), "fpc_kmeans_finalize")
+    try:
+        with torch.cuda.device(dev):
+            N.check(N.lib().fpc_kmeans_assign_accumulate(
+                data_dev.data_ptr(), n, cb_dev.data_ptr(), K, acc.data_ptr(), acc.data_ptr() + K * 17 * 8, None,
+                ws.data_ptr(), ws.numel(), N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
+            if fpc_dist.is_distributed(group):
+                fpc_dist._dist().all_reduce(acc, op=fpc_dist._dist().ReduceOp.SUM, group=group)
+            # n_total = 0: nb_vectors is the sum of the (all-reduced) counts, taken on the device
+            N.check(N.lib().fpc_kmeans_finalize_acc(acc.data_ptr(), K, 0.0, out.data_ptr(), stats.data_ptr(),
+                                                    N.current_stream(dev)), "fpc_kmeans_finalize_acc")
+    except Exception:
+        acc.zero_()         # never leave a half-filled accumulator behind
+        raise
     return out, stats, stats[4]
 
 

@@ -249,6 +249,12 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
  * iteration when the counts were all-reduced on the device. */
 int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, double n_total, double *d_cb_out,
                         double *d_stats, void *stream);
+
+/* The same on ONE accumulator  d_acc = [sums (K,17) | counts (K)]  -- K * 18 float64, the layout a single all-reduce
+ * message wants: fpc_kmeans_assign_accumulate takes d_acc and d_acc + 17 K, ranks all-reduce d_acc in place, and this
+ * call divides, writes the statistics and leaves d_acc ZEROED for the next Lloyd iteration (cb_func.py:71-100 with no
+ * memset / pack / unpack launches between the iterations).  n_total <= 0: the sum of the counts. */
+int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_out, double *d_stats, void *stream);
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 
@@ -300,6 +306,12 @@ int fpc_ceps2lpc(const float *d_ceps, long n, int stride, float *d_lpc, float *d
 int fpc_debug_set_phase_buffer(void *d_buf);
 
 int fpc_selftest_umma(const void *d_a_bf16, const void *d_b_bf16, int N, int K, float *d_out, void *stream);
+
+/* Self-test of the tensor-core distance screen (csrc/fpc_tc.cuh): scores[v][k] = ||c_k||^2 - 2 <x_v, c_k> of n <= 128
+ * vectors against K <= 1024 float64 centroids exactly as the screen of fpc_kmeans_assign_accumulate computes them
+ * (fp16-pair operands, tcgen05, fp32 accumulators), so a test can measure their error against float64.
+ * d_out: n x Kp floats (Kp = K rounded up to 128); d_pack: fpc_kmeans_workspace_bytes(n, K) bytes of scratch. */
+int fpc_selftest_tc_scores(const float *d_x, int n, const double *d_cb, int K, float *d_out, void *d_pack, void *stream);
 
 #if defined(__GNUC__)
 #pragma GCC visibility pop

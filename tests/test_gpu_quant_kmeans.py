@@ -131,3 +131,67 @@ def test_kmeans_device_resident(torch_cuda, oracle, synth):
         np.testing.assert_allclose(cbd.cpu().numpy(), cb, rtol=1e-11, atol=1e-300)
         cb = cbd.cpu().numpy()      # follow the device trajectory so rounding noise does not compound
     assert n == 30000
+
+
+def _tc_scores(torch, x, cb):
+    import fpc_native as N
+    n, K = x.shape[0], cb.shape[0]
+    Kp = (K + 127) // 128 * 128
+    xd = torch.from_numpy(np.ascontiguousarray(x, np.float32)).cuda()
+    cd = torch.from_numpy(np.ascontiguousarray(cb, np.float64)).cuda()
+    out = torch.zeros((n, Kp), dtype=torch.float32, device="cuda")
+    ws = torch.empty(N.lib().fpc_kmeans_workspace_bytes(n, K), dtype=torch.uint8, device="cuda")
+    N.check(N.lib().fpc_selftest_tc_scores(xd.data_ptr(), n, cd.data_ptr(), K, out.data_ptr(), ws.data_ptr(),
+                                           N.current_stream()), "fpc_selftest_tc_scores")
+    torch.cuda.synchronize()
+    return out.cpu().numpy()[:, :K]
+
+
+@pytest.mark.parametrize("scale_x,scale_c", [(0.1, 0.1), (0.03, 0.1), (1.0, 0.05), (1e-4, 0.1), (3.0, 0.1)])
+def test_tc_screen_score_error_budget(torch_cuda, scale_x, scale_c):
+    """The tensor-core screen (fp16-pair operands, tcgen05, fp32 accumulation) against float64: the error of a score
+    must stay far inside the decision slack 2^-15 R = 512 u R, R = (||x|| + Cmax)^2, u = 2^-24 (csrc/fpc_tc.cuh budgets
+    <= 10 u R for the operand format; the rest is the tensor core's accumulation, which is what this test measures)."""
+    g = np.random.Generator(np.random.Philox(key=31))
+    K = 1024
+    cb = g.standard_normal((K, 17)) * scale_c
+    cb[7] = 0.0
+    cb[8, :] = 1e-6 * scale_c                       # tiny entries: fp16 sub-normal hi / lo parts
+    x = (g.standard_normal((128, 17)) * scale_x).astype(np.float32)
+    x[3] = 0.0
+    x[4, 1:] = 0.0
+    s = _tc_scores(torch_cuda, x, cb).astype(np.float64)
+    cf = cb.astype(np.float32).astype(np.float64)  # the screen sees the fp32 rounding of the book (budgeted separately)
+    exact = (cf * cf).sum(1)[None, :] - 2.0 * x.astype(np.float64) @ cf.T
+    cmax = np.sqrt((cb * cb).sum(1).max())
+    R = (np.sqrt((x.astype(np.float64) ** 2).sum(1)) + cmax) ** 2
+    err_u = np.abs(s - exact) / (R[:, None] * 2.0 ** -24)
+    print("\ntensor-core screen, |x| ~ %g, |c| ~ %g: max score error %.2f u R, mean %.3f u R" % (
+        scale_x, scale_c, err_u.max(), err_u.mean()))
+    assert err_u.max() <= 64.0                     # a quarter of the slack per comparison would be 128 u R
+
+
+@pytest.mark.parametrize("K", [128, 200, 513, 1024])
+def test_kmeans_tc_adversarial_vs_oracle(torch_cuda, oracle, synth, K):
+    """The tensor-core assignment against the oracle on data built to sit on decision boundaries: exact duplicates of
+    centroids, midpoints of centroid pairs (exact distance ties up to rounding), vectors far outside the format's
+    range (|x| >> |c|), all-zero vectors, and a book with a cluster of near-identical centroids."""
+    from quantization import cb_func
+    g = np.random.Generator(np.random.Philox(key=40 + K))
+    cb = g.standard_normal((K, 17)) * 0.1
+    cb[10:20] = cb[9] + g.standard_normal((10, 17)) * 1e-7      # near-identical cluster
+    cb[21] = cb[20]
+    base = synth.make_kmeans_data(20000, seed=33, n_components=64)
+    mids = (0.5 * (cb[g.integers(0, K, 2000)] + cb[g.integers(0, K, 2000)])).astype(np.float32)
+    on = cb[g.integers(0, K, 2000)].astype(np.float32)
+    far = (g.standard_normal((500, 17)) * 300.0).astype(np.float32)           # leaves the fp16-pair range
+    tiny = (g.standard_normal((500, 17)) * 1e-9).astype(np.float32)
+    zero = np.zeros((37, 17), np.float32)
+    data = np.ascontiguousarray(np.concatenate([base, mids, on, far, tiny, zero]))
+    idx = cb_func.find_nearest(data, cb)
+    ref = oracle.find_nearest(data, cb)
+    bad = np.flatnonzero(idx != ref)
+    assert len(bad) == 0, "%d of %d assignments differ, first at row %d: %d vs %d" % (len(bad), len(data), bad[0], idx[bad[0]], ref[bad[0]])
+    new = cb_func.update(data, cb, K, verbose=False)
+    want = oracle.kmeans_update(data, cb)
+    np.testing.assert_allclose(new, want, rtol=CENTROID_RTOL, atol=1e-300)

@@ -98,6 +98,15 @@ struct PackedVq {        // one VQ codebook file
     long long off_n[2];   // stage s squared norms [Kp], padded with 3e38
     long long off_g;      // Gram table [K][Kp] = 2 * <c0_k0, c1_k1>   (2-stage books)
     long long off_cmax;   // float[2]: upper bounds of max_k ||c_k|| per stage
+    // tensor-core screen (fpc_tc.cuh, fpc_vq_tc.cuh): per stage the fp16-pair B operand image, Kp64 rows in tiles of 64
+    // codewords (8 KB each, four 2 KB K-slabs), scaled by the power of two beta_s = ((float *)(base + off_tcbeta))[s]
+    // The images are stored kWeightReplicas times (every CTA streams them every frame: one copy would be an L2 hot
+    // spot, exactly as for the weights); replica r starts b_rep_stride bytes after replica r - 1, and the stages of
+    // one replica are contiguous.
+    long long off_b[2];
+    long long off_tcbeta;
+    long long b_rep_stride;
+    int Kp64, pad_;
 };
 struct PackedScl {
     int dtype, n;
@@ -110,6 +119,7 @@ struct PackedCodebooks {  // header at offset 0 of the packed codebook image
 constexpr size_t kCbHeaderBytes = 512;
 constexpr size_t kCbVqMaxBytes = (size_t)2 * FPC_MAX_VQ_ENTRIES * kDim * 8 * 2    // both layouts, f64
                                  + (size_t)2 * (kDim + 1) * FPC_MAX_VQ_ENTRIES * 4   // fp32 shadows + norms
+                                 + (size_t)8 * 2 * FPC_MAX_VQ_ENTRIES * 128          // tensor-core operand images, 8 replicas
                                  + (size_t)FPC_MAX_VQ_ENTRIES * FPC_MAX_VQ_ENTRIES * 4 + 8192;   // Gram table, cmax, alignment slack
 constexpr size_t kCbSclMaxBytes = (size_t)FPC_MAX_SCL_ENTRIES * 8;
 constexpr size_t kPackedCbBytes = kCbHeaderBytes + 2 * kCbVqMaxBytes + 2 * kCbSclMaxBytes;

@@ -16,7 +16,7 @@
 // Roles (384 threads): warps 0-7 compute -- gate epilogue straight from TMEM (tcgen05.ld; lane quarter
 // = warp % 4, column half = warp / 4), then FC, residual, thresholds, scalar quantiser, m-best VQ and
 // the feedback; warp 8 lane 0 streams the packed bf16 weight image (1.35 MB per frame, L2 resident)
-// through a 4-stage x 12 KB ring with bulk async copies; warp 9 lane 0 issues the MMAs.  Hand-offs are
+// through a 3-stage x 12 KB ring with bulk async copies; warp 9 lane 0 issues the MMAs.  Hand-offs are
 // mbarriers: ring full/empty (TMA tx bytes / tcgen05.commit), accumulator full/empty, activations
 // ready (generic-proxy writes fenced to the async proxy).
 #include "fpc_common.cuh"
@@ -24,12 +24,13 @@
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
 #include "fpc_vq_screen.cuh"
+#include "fpc_vq_tc.cuh"
 #include "fpc_encode.cuh"
 #include "fpc_umma.cuh"
 
 namespace fpc {
 
-constexpr int kBStages = 4;
+constexpr int kBStages = 3;                                   // weight ring depth (a fourth stage bought nothing; the VQ screen uses the 12 KB)
 constexpr int kBTileBytes = 128 * 16 * 2;                      // one A tile: 128 gate rows x K = 16, bf16
 constexpr int kBStageBytes = 3 * kBTileBytes;                  // r, z and the third gate (n_i or n_h)
 constexpr int kBG1Steps = 2 + kH1 / 16;                        // 26: x padded to 32, then h1
@@ -121,8 +122,26 @@ template <int NU> struct SmemB {
     // misc: m1[NU] m2[NU] (float), idx0/idx1/idx2[NU], listA[NU], listB[NU] (int), counts[4], tmem base, pad
     static constexpr int offBars = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;
     static constexpr int kNumBars = 2 * kBStages + 3;
-    static constexpr int total = ((offBars + kNumBars * 8 + 127) / 128) * 128;
+    static constexpr int kBase = ((offBars + kNumBars * 8 + 127) / 128) * 128;
     static constexpr int kScratchBytes = kX1Bytes;   // the dead [x | h1] tile doubles as VQ scratch
+    // Tensor-core VQ screen (fpc_vq_tc.cuh).  The A tiles live in the scratch when they fit (64-utterance tiles: 3 x 16 KB
+    // of 53 248), else behind the control block; then the small tables, the scan partials and a codebook ring of two
+    // 8 KB chunks.
+    static constexpr int kMtMax = (5 * NU + 127) / 128;
+    static constexpr int kABytes = kMtMax * tc::kTileBytes;
+    static constexpr bool kAInScratch = kABytes <= kScratchBytes;
+    static constexpr bool kSmallInScratch = kAInScratch && kABytes + vq_tc_small_bytes(NU) <= kScratchBytes;
+    static constexpr int offVqSh = kBase;
+    static constexpr int offVqSmall = offVqSh + 512;                                                // used when !kSmallInScratch
+    static constexpr int offVqA = offVqSmall + (kSmallInScratch ? 0 : ((vq_tc_small_bytes(NU) + 127) / 128) * 128);   // used when !kAInScratch
+    static constexpr int offPart = offVqA + (kAInScratch ? 0 : kABytes);
+    static constexpr int offBring = offPart + vq_tc_part_bytes(kMtMax);
+    // Two chunks, not as many as fit: what the CTA leaves of the 228 KB is L1, and L1 is where the register spills of this
+    // kernel live (with 227 KB of shared memory every spill reload was an L2 round trip: the MMA issuer then needed
+    // 1.4 k cycles per chunk, tools/phase_profile.py trace).
+    static constexpr int kNB = 2;
+    static constexpr int total = offBring + kNB * kVtChunkBytes;
+    static_assert(total <= 227 * 1024, "shared memory");
 };
 
 __device__ __forceinline__ float tanh_fast(float x)
@@ -210,23 +229,32 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     const int warp = tid >> 5, lane = tid & 31;
     const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
+    VqTcShared<S::kNB> *vsh = reinterpret_cast<VqTcShared<S::kNB> *>(smem + S::offVqSh);
+    static_assert(sizeof(VqTcShared<S::kNB>) <= 512, "control block");
     if (tid == 0) {
-        for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 1); }
-        mbar_init(acc_full, 1);
+        for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }      // three issuing warps
+        mbar_init(acc_full, 3);
         mbar_init(acc_empty, kComputeThreads / 32);
         mbar_init(act_ready, kComputeThreads / 32);
+        vq_tc_init<S::kNB>(vsh, kComputeThreads / 32);
         mbar_fence_init();
     }
-    if (warp == 0) umma::tmem_alloc(tmem_slot, 4 * NU);
+    // all 512 columns: the gate accumulators use 4 NU of them; the VQ screen uses all of them while the gate
+    // accumulators are dead (between the GRU 2 epilogue and the next frame's activations)
+    if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
     umma::fence_before_sync();
     __syncthreads();
     umma::fence_after_sync();
     const uint32_t tb = *tmem_slot;
+    if (tid == 0) {
+        vsh->tmem_base = tb;       // the VQ screen reads it from its control block
+        if (P.prof != nullptr && blockIdx.x == 0) vsh->trace = P.prof + 8192;      // debug trace (first 64 chunks / units)
+    }
 
     // ---------------- dedicated warpgroup: TMA producer and MMA issuer ----------------
     if (warp >= kComputeThreads / 32) {
-        // 256 x 216 + 128 x 64 = 63 488 <= 384 x 168 (the launch allocation): the increase can always be granted
-        asm volatile("setmaxnreg.dec.sync.aligned.u32 64;");
+        // 256 x 216 + 128 x 72 = 64 512 = 384 x 168 (the launch allocation): the increase can always be granted
+        asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
         if (warp == kComputeThreads / 32 && lane == 0) {
             const long long total = (long long)my_tiles * (P.f1 - P.f0) * kBStepsPerFrame;
             const char *src = reinterpret_cast<const char *>(P.wstream);
@@ -239,13 +267,20 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                 if (++gf == kBStepsPerFrame) gf = 0;
                 if (++s == kBStages) { s = 0; ++wraps; }
             }
-        } else if (warp == kComputeThreads / 32 + 1 && lane == 0) {
+        } else if (warp > kComputeThreads / 32) {
+            // MMA issuers: warps 9, 10, 11, one GATE each (r, z, n -- separate accumulators, so the split does not touch
+            // any summation order).  A single thread needs ~100-200 cycles per tcgen05 instruction (descriptor moves to
+            // the uniform datapath, issue), which made the 330 MMAs of a frame as long as the whole GRU phase; three
+            // warps issue their 110 concurrently.  Each warp runs its loop converged and one elected lane issues
+            // (fpc_umma.cuh).  For the VQ screen warps 9 and 11 issue alternate chunks and warp 10 streams the codebook.
+            const int gate = warp - (kComputeThreads / 32 + 1);          // 0 = r, 1 = z, 2 = n
             const uint32_t idesc = umma::instr_desc_bf16(128, NU);
             const uint32_t ring_a = smem_u32(smem + S::offRing);
             const uint32_t x1a[2] = {smem_u32(x1[0]), smem_u32(x1[1])};
             const uint32_t h2a = smem_u32(h2t);
             int s = 0;
             uint32_t ph = 0, n_act = 0, n_acc = 0;
+            VqTcCount vn{0u, 0u, 0u, 0u};
             for (int tile = 0; tile < my_tiles; ++tile) {
                 int cur = 0;
                 for (int fr = P.f0; fr < P.f1; ++fr) {
@@ -257,16 +292,15 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                         for (int i = 0; i < kBG1Steps; ++i) {
                             mbar_wait(&full[s], ph);
                             umma::fence_after_sync();
-                            const uint32_t a0 = ring_a + s * kBStageBytes;
+                            const uint32_t a0 = ring_a + s * kBStageBytes + gate * kBTileBytes;
                             const uint64_t bd = umma::smem_desc(x1a[cur] + (uint32_t)(2 * i) * (NU * 16), NU);
-                            umma::mma_bf16(tb + 0 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                            umma::mma_bf16(tb + 1 * NU, umma::smem_desc(a0 + kBTileBytes, 128), bd, idesc, i > 0);
-                            if (i < 2) umma::mma_bf16(tb + 2 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 0);
-                            else umma::mma_bf16(tb + 3 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 2);
-                            umma::commit(&empty[s]);
+                            if (gate < 2) umma::mma_bf16_elect(tb + gate * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                            else if (i < 2) umma::mma_bf16_elect(tb + 2 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                            else umma::mma_bf16_elect(tb + 3 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 2);
+                            umma::commit_elect(&empty[s]);
                             if (++s == kBStages) { s = 0; ph ^= 1u; }
                         }
-                        umma::commit(acc_full);
+                        umma::commit_elect(acc_full);
                     }
                     // ---- GRU 2: input h1' (the other [x | h1] tile), hidden h2 ----
                     mbar_wait(act_ready, n_act & 1u); ++n_act;
@@ -275,20 +309,30 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     for (int i = 0; i < kBG2Steps; ++i) {
                         mbar_wait(&full[s], ph);
                         umma::fence_after_sync();
-                        const uint32_t a0 = ring_a + s * kBStageBytes;
+                        const uint32_t a0 = ring_a + s * kBStageBytes + gate * kBTileBytes;
                         const bool xp = i < kH1 / 16;
                         const uint32_t baddr = xp ? x1a[cur ^ 1] + (uint32_t)(4 + 2 * i) * (NU * 16)
                                                   : h2a + (uint32_t)(2 * (i - kH1 / 16)) * (NU * 16);
                         const uint64_t bd = umma::smem_desc(baddr, NU);
-                        umma::mma_bf16(tb + 0 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                        umma::mma_bf16(tb + 1 * NU, umma::smem_desc(a0 + kBTileBytes, 128), bd, idesc, i > 0);
-                        if (xp) umma::mma_bf16(tb + 2 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > 0);
-                        else umma::mma_bf16(tb + 3 * NU, umma::smem_desc(a0 + 2 * kBTileBytes, 128), bd, idesc, i > kH1 / 16);
-                        umma::commit(&empty[s]);
+                        if (gate < 2) umma::mma_bf16_elect(tb + gate * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                        else if (xp) umma::mma_bf16_elect(tb + 2 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
+                        else umma::mma_bf16_elect(tb + 3 * NU, umma::smem_desc(a0, 128), bd, idesc, i > kH1 / 16);
+                        umma::commit_elect(&empty[s]);
                         if (++s == kBStages) { s = 0; ph ^= 1u; }
                     }
-                    umma::commit(acc_full);
+                    umma::commit_elect(acc_full);
                     cur ^= 1;
+                    // the searches of this frame: stages of the codebooks as published by the compute warps
+                    if (P.mode == kModeQuantize) {
+                        bool done = false;
+                        if (gate == 1) {
+                            if (lane == 0)
+                                while (!done) done = vq_tc_produce_phase<S::kNB>(vsh, P.cb, vn);
+                            __syncwarp();
+                        } else {
+                            while (!done) done = vq_tc_issue_phase<S::kNB>(vsh, tb, vn, lane, gate >> 1);
+                        }
+                    }
                 }
             }
         }
@@ -463,14 +507,26 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     named_bar_sync(1, kComputeThreads);
                     const int nA = counts[0], nB = counts[1];
                     char *scratch = reinterpret_cast<char *>(x1[cur]);   // old [x | h1]: dead once GRU 1 has finished
-                    // one call site for both books (above / below threshold): a single inlined copy of the search
+                    VqTcMem vmem;
+                    unsigned char *abase = S::kAInScratch ? reinterpret_cast<unsigned char *>(scratch) : smem + S::offVqA;
+                    vmem.a = abase;
+                    vmem.small = S::kSmallInScratch ? scratch + S::kABytes : reinterpret_cast<char *>(smem) + S::offVqSmall;
+                    vmem.part = smem + S::offPart;
+                    vmem.bring = smem + S::offBring;
+                    vmem.scratch = scratch;
+                    vmem.scratch_bytes = S::kScratchBytes;
+                    vmem.tail = reinterpret_cast<int *>(smem + S::offPart);   // idle by the time the fallback runs
+                    // one call site for both books (above / below threshold): a single inlined copy of the search.  The
+                    // helper roles are owed exactly one publication with last = 1 per frame.
+                    const bool tcB = nB > 0 && cbh->bl.K >= 64;
 #pragma unroll 1
                     for (int book = 0; book < 2; ++book) {
                         const int nrows = book ? nB : nA;
                         if (nrows > 0)
-                            vq_dispatch_screened(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, NU, rs, rq, idx1s, idx2s,
-                                                 scratch, S::kScratchBytes, tid, prof ? pt + kPhVqDbg : nullptr);
+                            vq_tc_dispatch<NU, S::kNB>(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, rs, rq, idx1s, idx2s,
+                                                       vmem, vsh, (book == 1 || !tcB) ? 1 : 0, tid, prof ? pt + kPhVqDbg : nullptr);
                     }
+                    if (!(nA > 0 && cbh->vq.K >= 64) && !tcB) vq_tc_publish_idle<S::kNB>(vsh, tid);
                 }
             } else {
                 named_bar_sync(1, kComputeThreads);
@@ -550,7 +606,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
         for (int i = 0; i < kPhCount; ++i) atomicAdd(reinterpret_cast<unsigned long long *>(P.prof) + (size_t)blockIdx.x * kPhCount + i, (unsigned long long)pt[i]);
 #undef FPC_PHASE
     named_bar_sync(1, kComputeThreads);
-    if (warp == 0) umma::tmem_dealloc(tb, 4 * NU);
+    if (warp == 0) umma::tmem_dealloc(tb, 512);
 }
 
 template <int NU>

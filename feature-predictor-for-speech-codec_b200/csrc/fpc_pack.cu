@@ -4,6 +4,7 @@
 // quantization/vq_func.py:141,171.
 #include "fpc_common.cuh"
 #include "fpc_encode.cuh"
+#include "fpc_tc.cuh"
 
 namespace fpc {
 
@@ -128,6 +129,48 @@ __global__ void pack_gram_kernel(const T *__restrict__ c0, const T *__restrict__
     G[t] = (float)(2.0 * acc);
 }
 
+// Tensor-core screen of the m-best search (fpc_vq_tc.cuh): the B operand image of one stage.  One CTA: largest |c|
+// -> power-of-two scale beta, then every codeword as an fp16-pair row (fpc_tc.cuh) in tiles of 64 rows; rows K..Kp64-1
+// are padding that can never win (norm entries 3 x 65504).  Entries 54..56 hold 1024: the vector side multiplies them
+// by its offset / 1024 (stage 0 of two-stage books).
+template <typename T>
+__global__ void __launch_bounds__(1024, 1)
+pack_tc_image_kernel(const T *__restrict__ src /* [K][17] */, int K, int Kp64, unsigned char *__restrict__ image0, long long rep_stride,
+                     float *__restrict__ beta_out)
+{
+    unsigned char *__restrict__ image = image0 + (size_t)blockIdx.x * rep_stride;       // one CTA per replica
+    __shared__ float s_red[32];
+    float amax = 0.0f;
+    for (int i = threadIdx.x; i < K * kDim; i += blockDim.x) amax = fmaxf(amax, __double2float_ru(fabs((double)src[i])));
+    for (int off = 16; off > 0; off >>= 1) amax = fmaxf(amax, __shfl_xor_sync(0xffffffffu, amax, off));
+    if ((threadIdx.x & 31) == 0) s_red[threadIdx.x >> 5] = amax;
+    __syncthreads();
+    amax = 0.0f;
+    for (int w = 0; w < (int)(blockDim.x >> 5); ++w) amax = fmaxf(amax, s_red[w]);
+    const float beta = tc::scale_for(amax);
+    if (threadIdx.x == 0 && blockIdx.x == 0) *beta_out = beta;
+    const __half k1024 = __float2half_rn(1024.0f);
+    for (int k = threadIdx.x; k < Kp64; k += blockDim.x) {
+        float xs[kDim];
+        __half n0, n1, n2;
+        if (k < K) {
+            double nn = 0.0;
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) {
+                const double c = (double)src[(size_t)k * kDim + d];
+                xs[d] = (float)(c * (double)beta);
+                nn += c * c;
+            }
+            tc::split3((float)(nn * (double)beta * (double)beta), n0, n1, n2);
+        } else {
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) xs[d] = 0.0f;
+            n0 = n1 = n2 = __float2half_rn(tc::kPadNorm);
+        }
+        tc::store_row<false, 64>(image + (size_t)(k >> 6) * (64 * tc::kK * 2), k & 63, xs, n0, n1, n2, k1024, k1024, k1024);
+    }
+}
+
 template <typename T>
 __global__ void copy_kernel(const T *__restrict__ src, int n, T *__restrict__ dst)
 {
@@ -160,6 +203,7 @@ static int pack_one_vq(const void *src, int dtype, int stages, int K, char *base
     h.dtype = dtype; h.stages = stages; h.K = K; h.Kp = (K + 3) & ~3;
     h.off_t[0] = h.off_t[1] = h.off_r[0] = h.off_r[1] = 0;
     h.off_f[0] = h.off_f[1] = h.off_n[0] = h.off_n[1] = h.off_g = h.off_cmax = 0;
+    h.off_b[0] = h.off_b[1] = 0; h.off_tcbeta = 0; h.b_rep_stride = 0; h.Kp64 = (K + 63) & ~63; h.pad_ = 0;
     if (stages == 0) return FPC_OK;
     size_t es = dtype == FPC_F32 ? 4 : 8;
     size_t one = (((size_t)K * kDim * es) + 255) / 256 * 256;
@@ -193,6 +237,25 @@ static int pack_one_vq(const void *src, int dtype, int stages, int K, char *base
             pack_screen_kernel<double><<<(Kp + 127) / 128, 128, 0, st>>>((const double *)src + (size_t)s * K * kDim, K, Kp,
                                                                           (float *)(base + h.off_f[s]), (float *)(base + h.off_n[s]), cm);
         FPC_LAUNCH_CHECK();
+    }
+    // ---- tensor-core operand images and their scales ----
+    {
+        const long long off_beta = (long long)cursor; cursor += 256;
+        h.off_tcbeta = off_beta;
+        const size_t one_image = (size_t)h.Kp64 * tc::kK * 2;
+        h.b_rep_stride = (long long)(stages * one_image);
+        for (int s = 0; s < stages; ++s) {
+            h.off_b[s] = (long long)(cursor + s * one_image);
+            float *bo = (float *)(base + off_beta) + s;
+            if (dtype == FPC_F32)
+                pack_tc_image_kernel<float><<<kWeightReplicas, 1024, 0, st>>>((const float *)src + (size_t)s * K * kDim, K, h.Kp64,
+                                                                               (unsigned char *)(base + h.off_b[s]), h.b_rep_stride, bo);
+            else
+                pack_tc_image_kernel<double><<<kWeightReplicas, 1024, 0, st>>>((const double *)src + (size_t)s * K * kDim, K, h.Kp64,
+                                                                                (unsigned char *)(base + h.off_b[s]), h.b_rep_stride, bo);
+            FPC_LAUNCH_CHECK();
+        }
+        cursor += (size_t)kWeightReplicas * stages * one_image;
     }
     if (stages == 2) {
         h.off_g = (long long)cursor; cursor += (((size_t)K * Kp * 4) + 255) / 256 * 256;

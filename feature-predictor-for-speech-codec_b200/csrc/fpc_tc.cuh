@@ -12,7 +12,9 @@
 //     x c  ~  xh ch + xh cl + xl ch          (dropped: xl cl <= 2^-22 |x c|)
 // Per dimension d the K extent holds   A side (vectors): xh, xh, xl    B side (codewords): ch, cl, ch
 // i.e. 51 entries for 17 dimensions; entries 51..53 carry the norm: A side 1, 1, 1; B side the 3-way fp16 split of
-// beta^2 ||c||^2; entries 54..63 are zero.  K = 64 = four tcgen05 K-slabs, 128 bytes per row.
+// beta^2 ||c||^2; entries 54..56 may carry a per-vector offset (A side: 3-way split of offset / 1024, B side: 1024) that
+// makes every score of a vector positive, which the key-packed top-k scan of the m-best search needs; entries 57..63 are
+// zero.  K = 64 = four tcgen05 K-slabs, 128 bytes per row.
 // Values are scaled by a power of two beta (exact) so that the largest |c| lies in [4, 8): fp16 then keeps an absolute
 // resolution of 2^-25 (subnormal hi/lo parts included), far below the 2^-22 relative target at that scale, and the
 // vector side  -2 beta x  may be up to 1024 (an x 128 times the largest codeword entry) before it leaves the format --
@@ -76,10 +78,12 @@ __device__ __forceinline__ void split2(float v, __half &hi, __half &lo)
     lo = __float2half_rn(__fsub_rn(v, __half2float(hi)));
 }
 
-// Writes row r of a 128-row operand tile from the 17 scaled values xs (vector side: -2 beta x; codeword side: beta c)
-// and the three norm entries (vector side: 1, 1, 1; codeword side: split of beta^2 ||c||^2).
-template <bool kVectorSide>
-__device__ __forceinline__ void store_row(unsigned char *tile, int r, const float (&xs)[kDim], __half n0, __half n1, __half n2)
+// Writes row r of a kRows-row operand tile from the 17 scaled values xs (vector side: -2 beta x; codeword side: beta c),
+// the three norm entries 51..53 (vector side: 1, 1, 1; codeword side: split of beta^2 ||c||^2) and the three offset
+// entries 54..56 (o0..o2; callers that add no per-vector offset pass zeros).
+template <bool kVectorSide, int kRows = kTileRows>
+__device__ __forceinline__ void store_row(unsigned char *tile, int r, const float (&xs)[kDim], __half n0, __half n1, __half n2,
+                                          __half o0 = __ushort_as_half(0), __half o1 = __ushort_as_half(0), __half o2 = __ushort_as_half(0))
 {
     __half e[kK];
 #pragma unroll
@@ -91,14 +95,15 @@ __device__ __forceinline__ void store_row(unsigned char *tile, int r, const floa
         e[3 * d + 2] = kVectorSide ? lo : hi;
     }
     e[51] = n0; e[52] = n1; e[53] = n2;
+    e[54] = o0; e[55] = o1; e[56] = o2;
 #pragma unroll
-    for (int i = 54; i < kK; ++i) e[i] = __float2half_rn(0.0f);
+    for (int i = 57; i < kK; ++i) e[i] = __float2half_rn(0.0f);
 #pragma unroll
     for (int c = 0; c < kK / 8; ++c) {
         uint4 w;
         w.x = pack_h2(e[8 * c], e[8 * c + 1]); w.y = pack_h2(e[8 * c + 2], e[8 * c + 3]);
         w.z = pack_h2(e[8 * c + 4], e[8 * c + 5]); w.w = pack_h2(e[8 * c + 6], e[8 * c + 7]);
-        *reinterpret_cast<uint4 *>(tile + (size_t)c * (kTileRows * 16) + (size_t)r * 16) = w;
+        *reinterpret_cast<uint4 *>(tile + (size_t)c * (kRows * 16) + (size_t)r * 16) = w;
     }
 }
 

@@ -64,6 +64,28 @@ __device__ __forceinline__ void mma_bf16(uint32_t tmem_d, uint64_t adesc, uint64
         ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
         : "memory");
 }
+// The same, executed by a whole converged warp: one elected lane issues.  The issuing code then stays warp-uniform, so
+// the compiler keeps the descriptors on the uniform datapath; issued from an `if (lane == 0)` region every operand goes
+// through an ELECT / R2UR.BROADCAST sequence first and one MMA costs ~150 cycles of issue time (measured: the 330 MMAs
+// of a frame took as long as the whole GRU phase).
+__device__ __forceinline__ void mma_bf16_elect(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate)
+{
+    asm volatile(
+        "{\n\t.reg .pred p, q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "@q tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t}"
+        ::"r"(tmem_d), "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void commit_elect(uint64_t *bar)
+{
+    asm volatile(
+        "{\n\t.reg .pred q;\n\t"
+        "elect.sync _|q, 0xffffffff;\n\t"
+        "@q tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];\n\t}"
+        ::"r"(smem_u32(bar)) : "memory");
+}
 // all MMAs issued so far by this thread arrive on the mbarrier when they have completed
 __device__ __forceinline__ void commit(uint64_t *bar)
 {

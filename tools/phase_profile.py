@@ -24,7 +24,7 @@ with torch.no_grad():
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); res = m.encode_device(cfg, feat, None, l1, l2); e1.record(); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(None)
-c = buf.cpu().numpy().astype(np.float64).reshape(-1, 16)
+c = buf.cpu().numpy().astype(np.float64)[:8192].reshape(-1, 16)
 c = c[c[:, 5] > 0]
 fr = c[:, 5:6]
 names = ["gru", "fc+residual", "thresholds+scalar", "vq", "feedback/out"]
@@ -37,4 +37,13 @@ for i, n_ in enumerate(names):
 print("vq rows %d, sent to the exact search %d (%.2f %%)" % (c[:, 6].sum(), c[:, 7].sum(), 100 * c[:, 7].sum() / max(c[:, 6].sum(), 1)))
 for i, n_ in enumerate(["margins", "stage-0 screen", "stage-0 select", "last-stage screen", "merge+gather", "exact fallback"]):
     print("     vq/%-18s mean %8.0f cycles/frame" % (n_, (c[:, 8 + i] / fr[:, 0]).mean()))
+print("     vq/wait for MMA units: stage 0 %8.0f, last stage %8.0f cycles/frame (thread 0)" % ((c[:, 14] / fr[:, 0]).mean(), (c[:, 15] / fr[:, 0]).mean()))
 print("above-threshold fractions: c0 %.3f  c1..17 %.3f" % (res.ind1.mean().item(), res.ind2.mean().item()))
+
+if bf16:
+    t = buf.cpu().numpy()[8192:8192 + 512].astype(np.int64)
+    if t[0]:
+        t0 = t[0]
+        print("trace CTA 0 (cycles from the first codebook copy): chunk: copy issued | data landed | units free | MMAs issued | commits issued")
+        for c in range(0, 34):
+            print("  %2d: %7d %7d %7d %7d %7d" % (c, t[c] - t0, t[64 + c] - t0, t[192 + c] - t0, t[320 + c] - t0, t[128 + c] - t0))

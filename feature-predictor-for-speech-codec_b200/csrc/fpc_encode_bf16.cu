@@ -30,7 +30,7 @@
 
 namespace fpc {
 
-constexpr int kBStages = 3;                                   // weight ring depth (a fourth stage bought nothing; the VQ screen uses the 12 KB)
+constexpr int kBStages = 3;                                   // weight ring depth (a fourth stage measured no faster; the VQ screen and the L1 use the 12 KB)
 constexpr int kBTileBytes = 128 * 16 * 2;                      // one A tile: 128 gate rows x K = 16, bf16
 constexpr int kBStageBytes = 3 * kBTileBytes;                  // r, z and the third gate (n_i or n_h)
 constexpr int kBG1Steps = 2 + kH1 / 16;                        // 26: x padded to 32, then h1
@@ -120,7 +120,8 @@ template <int NU> struct SmemB {
     static constexpr int offRq = offRs + NU * kLdR * 4;
     static constexpr int offMisc = offRq + NU * 20 * 4;
     // misc: m1[NU] m2[NU] (float), idx0/idx1/idx2[NU], listA[NU], listB[NU] (int), counts[4], tmem base, pad
-    static constexpr int offBars = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;
+    static constexpr int offScl = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;      // both scalar tables, file dtype, 2 x 2 KB + {n, dtype} x 2
+    static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8 + 16;
     static constexpr int kNumBars = 2 * kBStages + 3;
     static constexpr int kBase = ((offBars + kNumBars * 8 + 127) / 128) * 128;
     static constexpr int kScratchBytes = kX1Bytes;   // the dead [x | h1] tile doubles as VQ scratch
@@ -348,6 +349,20 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
         for (int i = tid; i < kBiasFloats; i += kComputeThreads) bias[i] = tail[i];
         for (int i = tid; i < kFcFloats; i += kComputeThreads) wfc[(i >> 7) * kLdFcB + (i & 127)] = tail[kBiasFloats + i];
         if (tid < kFc) bfc[tid] = tail[kBiasFloats + kFcFloats + tid];
+        // the scalar tables (<= 256 levels each) next to the state: from global memory every scalar search paid L2 latencies
+        if (cbh != nullptr) {
+            unsigned char *sclbuf = smem + S::offScl;
+            const long long *src0 = reinterpret_cast<const long long *>(P.cb + cbh->scl.off);
+            const long long *src1 = reinterpret_cast<const long long *>(P.cb + cbh->blscl.off);
+            const int n0 = cbh->scl.n * (cbh->scl.dtype == FPC_F32 ? 4 : 8), n1 = cbh->blscl.n * (cbh->blscl.dtype == FPC_F32 ? 4 : 8);
+            for (int i = tid; i < (n0 + 7) / 8; i += kComputeThreads) reinterpret_cast<long long *>(sclbuf)[i] = src0[i];
+            for (int i = tid; i < (n1 + 7) / 8; i += kComputeThreads)
+                reinterpret_cast<long long *>(sclbuf + FPC_MAX_SCL_ENTRIES * 8)[i] = src1[i];
+            if (tid == 0) {
+                int *meta = reinterpret_cast<int *>(sclbuf + 2 * FPC_MAX_SCL_ENTRIES * 8);
+                meta[0] = cbh->scl.n; meta[1] = cbh->scl.dtype; meta[2] = cbh->blscl.n; meta[3] = cbh->blscl.dtype;
+            }
+        }
     }
     uint32_t n_full = 0;
     const bool prof = P.prof != nullptr && tid == 0;
@@ -443,10 +458,13 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
 
                 FPC_PHASE(kPhFc);
                 // ---- indicators (:201-212) and the scalar quantiser for c0 (:217-225) ----
-                for (int u = warp; u < NU; u += 8) {
+                // four lanes per utterance (256 threads = 64 utterances at once; a 32-utterance tile uses eight)
+                {
+                    constexpr int G = kComputeThreads / NU;                // 4 or 8 lanes per utterance
+                    const int u = tid / G, part = tid % G;
                     const bool valid = b0 + u < P.B;
                     float m1 = 0.0f, m2 = 0.0f;
-                    if (lane == 0 && valid) {
+                    if (part == 0 && valid) {
                         if (P.mask == nullptr) {
                             float sacc = 0.0f;
 #pragma unroll
@@ -459,27 +477,33 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                             m2 = __ldg(P.mask + fo * 2 + 1);
                         }
                     }
-                    m1 = __shfl_sync(0xffffffffu, m1, 0);
-                    m2 = __shfl_sync(0xffffffffu, m2, 0);
+                    m1 = __shfl_sync(0xffffffffu, m1, lane - part);
+                    m2 = __shfl_sync(0xffffffffu, m2, lane - part);
                     int i0 = -1;
-                    if (P.mode == kModeQuantize && valid) {
-                        const PackedScl &sb = (m1 != 0.0f) ? cbh->scl : cbh->blscl;
-                        if (sb.n > 0) {
-                            const float x0 = rs[u * kLdR + 3];
-                            float qv;
-                            if (sb.dtype == FPC_F32) {
-                                float qq;
-                                i0 = warp_scl_nearest<float>(reinterpret_cast<const float *>(P.cb + sb.off), sb.n, x0, lane, qq);
-                                qv = qq;
-                            } else {
-                                double qq;
-                                i0 = warp_scl_nearest<double>(reinterpret_cast<const double *>(P.cb + sb.off), sb.n, x0, lane, qq);
-                                qv = (float)qq;
-                            }
-                            if (lane == 0) rq[u * 20] = qv;
+                    float qv = 0.0f;
+                    bool coded = false;
+                    if (P.mode == kModeQuantize) {            // (every lane takes part in the group's shuffles)
+                        const int which = (m1 != 0.0f) ? 0 : 1;       // above / below threshold table (:217-225)
+                        const unsigned char *sclt = smem + S::offScl + which * (FPC_MAX_SCL_ENTRIES * 8);
+                        const int *meta = reinterpret_cast<const int *>(smem + S::offScl + 2 * FPC_MAX_SCL_ENTRIES * 8) + 2 * which;
+                        const int sn = valid ? meta[0] : 0, sdt = meta[1];
+                        const float x0 = rs[u * kLdR + 3];
+                        // (the tables of one warp's utterances may differ in dtype only between above / below: both branches are
+                        //  executed by the lanes that need them, with the group shuffles inside kept convergent per group)
+                        float qf = 0.0f;
+                        double qd = 0.0;
+                        const int if32 = group_scl_nearest<float, G>(reinterpret_cast<const float *>(sclt), sdt == FPC_F32 ? sn : 0, x0, part, qf);
+                        const int if64 = group_scl_nearest<double, G>(reinterpret_cast<const double *>(sclt), sdt == FPC_F32 ? 0 : sn, x0, part, qd);
+                        if (sn > 0) {
+                            coded = true;
+                            i0 = sdt == FPC_F32 ? if32 : if64;
+                            qv = sdt == FPC_F32 ? qf : (float)qd;
                         }
                     }
-                    if (lane == 0) { m1s[u] = m1; m2s[u] = m2; idx0s[u] = i0; idx1s[u] = -1; idx2s[u] = -1; }
+                    if (part == 0) {
+                        if (coded) rq[u * 20] = qv;
+                        m1s[u] = m1; m2s[u] = m2; idx0s[u] = i0; idx1s[u] = -1; idx2s[u] = -1;
+                    }
                 }
                 named_bar_sync(1, kComputeThreads);
 

@@ -96,4 +96,32 @@ __device__ __forceinline__ int warp_scl_nearest(const T *__restrict__ codes, int
     return bi;
 }
 
+// The same search by a group of `G` consecutive lanes (G = 4 or 8; every lane of the warp must call): lane `part` of
+// the group scans a contiguous quarter / eighth of the table in ascending order with strict < (first minimum), the group
+// then keeps the lexicographically smallest (distance, index).  Same arithmetic, same result as warp_scl_nearest; 32 / G
+// values are quantised per warp at once instead of one.
+template <typename T, int G>
+__device__ __forceinline__ int group_scl_nearest(const T *__restrict__ codes, int n, float x, int part, T &q)
+{
+    const int per = (n + G - 1) / G;
+    const int k0 = part * per, k1 = min(n, k0 + per);
+    const T xv = (T)x;
+    T best = Rn<T>::inf();
+    int bi = 0x7fffffff;
+    for (int k = k0; k < k1; ++k) {
+        const T t = Rn<T>::sub(xv, codes[k]);
+        const T d = Rn<T>::mul(t, t);
+        if (d < best || bi == 0x7fffffff) { best = d; bi = k; }
+    }
+#pragma unroll
+    for (int off = 1; off < G; off <<= 1) {
+        const T od = __shfl_xor_sync(0xffffffffu, best, off);
+        const int oi = __shfl_xor_sync(0xffffffffu, bi, off);
+        if (oi != 0x7fffffff && (bi == 0x7fffffff || od < best || (od == best && oi < bi))) { best = od; bi = oi; }
+    }
+    if (bi == 0x7fffffff) bi = 0;
+    q = codes[bi];
+    return bi;
+}
+
 }  // namespace fpc

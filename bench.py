@@ -639,10 +639,11 @@ def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
         res["K%d" % K] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "gpu_launches": int(fpc_native.launch_count() - n0),
                           "roofline": {"bound": "tensor", "kernel": "fpc::kmeans_assign_tc_kernel",
                                        "what": "distance screen as a tcgen05 GEMM (vectors x centroids, fp16-pair operands, K = 64)",
-                                       "achieved": 2.0 * n_total * K * 17 / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
-                                       "unit": "TFLOP/s", "frac": 2.0 * n_total * K * 17 / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                       "achieved": 2.0 * n_total / world * K * 17 / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
+                                       "unit": "TFLOP/s", "frac": 2.0 * n_total / world * K * 17 / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
+                                       "per": "GPU (the iteration includes the all-reduce and the finalize)",
                                        "algorithmic_flop_per_iter": 2.0 * n_total * K * 17,
-                                       "executed_tflops": 2.0 * n_total * kp * 64 / (ms * 1e-3) / 1e12},
+                                       "executed_tflops": 2.0 * n_total / world * kp * 64 / (ms * 1e-3) / 1e12},
                           "fp32_direct_form_tflops": flops / (ms * 1e-3) / 1e12,
                           "hbm_gbs": n_total * 68.0 / world / (ms * 1e-3) / 1e9,
                           "empty_clusters": float(stats[2].item()), "vectors_seen": int(n_seen)}

@@ -39,6 +39,7 @@ size_t encode_bf16_state_bytes(int B);
 int pack_weights_bf16(const fpc_weights *w, void *d_packed, cudaStream_t st);
 int num_sms();
 extern long long *g_phase_buffer;   // device pointer or null
-enum { kPhGru = 0, kPhFc = 1, kPhScalar = 2, kPhVq = 3, kPhOut = 4, kPhFrames = 5, kPhVqDbg = 6 /* 8 counters of the search */, kPhCount = 16 };
+enum { kPhGru = 0, kPhFc = 1, kPhScalar = 2, kPhVq = 3, kPhOut = 4, kPhFrames = 5, kPhVqDbg = 6 /* 10 counters of the search */,
+       kPhWaitX = 16 /* GEMM warps waiting for the tail */, kPhWaitH = 17 /* tail waiting for h2 */, kPhCount = 32 };
 
 }  // namespace fpc

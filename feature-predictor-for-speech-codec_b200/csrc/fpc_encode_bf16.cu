@@ -366,7 +366,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     }
     uint32_t n_full = 0;
     const bool prof = P.prof != nullptr && tid == 0;
-    long long pt[kPhCount] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt0 = 0;
+    long long pt[kPhCount] = {}, pt0 = 0;
 #define FPC_PHASE(ph) do { if (prof) { const long long t_ = clock64(); pt[ph] += t_ - pt0; pt0 = t_; } } while (0)
 
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {

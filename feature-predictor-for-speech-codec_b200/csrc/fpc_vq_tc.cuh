@@ -27,6 +27,14 @@
 #include "fpc_tc.cuh"
 #include "fpc_vq_screen.cuh"
 
+// The searches are out of line by default (one copy per dtype).  A kernel that moves registers between its warpgroups with
+// setmaxnreg.inc on a path that does NOT contain the call cannot use out-of-line device functions (cicc 12.9 crashes on
+// that combination, and a callee is compiled against the launch allocation anyway): it defines FPC_VQ_TC_OUTLINE as
+// __forceinline__ before including this file.
+#ifndef FPC_VQ_TC_OUTLINE
+#define FPC_VQ_TC_OUTLINE __noinline__
+#endif
+
 namespace fpc {
 
 constexpr int kVtUnits = 8;                          // TMEM units of 64 columns
@@ -42,7 +50,7 @@ __host__ __device__ constexpr int vq_tc_part_bytes(int mtmax) { return mtmax * 1
 struct VqTcCtl { int nchunks, mtiles, last, p_nchunks; uint32_t a_addr, ring_addr; long long b_off; };   // addresses: shared window
 
 // control block + barriers; lives in shared memory for the whole kernel (phase parities run across frames)
-template <int NB> struct VqTcShared {
+template <int NB, int UNITS = kVtUnits> struct VqTcShared {
     VqTcCtl ctl;
     // The compute warps' running counts and the TMEM base live HERE, not in registers: they would be live across the
     // whole frame loop, and the gate GEMM of the fp32 kernel has no register to spare (six more spilled inside its
@@ -51,19 +59,19 @@ template <int NB> struct VqTcShared {
     long long *trace;             // debug (tools/phase_profile.py): event times of the first phases of CTA 0, or null
     uint64_t go, ack;
     uint64_t b_full[NB], b_empty[NB];
-    uint64_t d_full[kVtUnits], d_empty[kVtUnits];
+    uint64_t d_full[UNITS], d_empty[UNITS];
 };
 struct VqTcCount { uint32_t go, b, u, ring; };       // running use counts of one role (phases, B chunks, TMEM units); ring address in use
 
-template <int NB>
-__device__ __forceinline__ void vq_tc_init(VqTcShared<NB> *sh, int compute_warps)
+template <int NB, int UNITS>
+__device__ __forceinline__ void vq_tc_init(VqTcShared<NB, UNITS> *sh, int compute_warps)
 {
     sh->cnt_go = sh->cnt_b = sh->cnt_u = 0u;
     sh->trace = nullptr;
     mbar_init(&sh->go, 1);
     mbar_init(&sh->ack, 3);            // two issuing warps + the streamer
     for (int i = 0; i < NB; ++i) { mbar_init(&sh->b_full[i], 1); mbar_init(&sh->b_empty[i], 1); }
-    for (int i = 0; i < kVtUnits; ++i) { mbar_init(&sh->d_full[i], 1); mbar_init(&sh->d_empty[i], compute_warps); }
+    for (int i = 0; i < UNITS; ++i) { mbar_init(&sh->d_full[i], 1); mbar_init(&sh->d_empty[i], compute_warps); }
 }
 
 // The helper threads sit at `go` for the whole predictor phase of every frame.  They wait with a long suspend-time
@@ -87,8 +95,8 @@ __device__ __forceinline__ void mbar_wait_idle(uint64_t *bar, uint32_t parity)
 }
 
 // ---- producer thread: one phase.  Returns true after the last phase of a frame ----
-template <int NB>
-__device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB> *sh, const char *__restrict__ cbbase, VqTcCount &n)
+template <int NB, int UNITS>
+__device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB, UNITS> *sh, const char *__restrict__ cbbase, VqTcCount &n)
 {
     mbar_wait_idle(&sh->go, n.go & 1u); ++n.go;
     const int nchunks = sh->ctl.p_nchunks, last = sh->ctl.last;
@@ -110,8 +118,8 @@ __device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB> *sh, const ch
 
 // ---- MMA issuer WARPS (two of them, `which` = 0 / 1, alternate chunks; all 32 lanes run the loop converged and one
 //      elected lane issues): one phase ----
-template <int NB>
-__device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB> *sh, uint32_t tb, VqTcCount &n, int lane, int which)
+template <int NB, int UNITS>
+__device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uint32_t tb, VqTcCount &n, int lane, int which)
 {
     mbar_wait_idle(&sh->go, n.go & 1u); ++n.go;
     const int nchunks = sh->ctl.nchunks, mtiles = sh->ctl.mtiles, last = sh->ctl.last;
@@ -134,8 +142,8 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB> *sh, uint32_t t
 #pragma unroll
         for (int m = 0; m < 3; ++m)
             if (m < mtiles) {
-                const uint32_t use = (n.u + m) / kVtUnits;
-                if (use > 0) mbar_wait(&sh->d_empty[(n.u + m) % kVtUnits], (use - 1) & 1u);
+                const uint32_t use = (n.u + m) / UNITS;
+                if (use > 0) mbar_wait(&sh->d_empty[(n.u + m) % UNITS], (use - 1) & 1u);
             }
         umma::fence_after_sync();
         if (lane == 0 && sh->trace && n.b < 64) sh->trace[192 + n.b] = clock64();
@@ -145,13 +153,13 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB> *sh, uint32_t t
 #pragma unroll
             for (int m = 0; m < 3; ++m)
                 if (m < mtiles)
-                    umma::mma_bf16_elect(tb + ((n.u + m) % kVtUnits) * 64u, adesc0 + (uint64_t)((m * tc::kTileBytes + ks * tc::kSlabBytes) >> 4),
+                    umma::mma_bf16_elect(tb + ((n.u + m) % UNITS) * 64u, adesc0 + (uint64_t)((m * tc::kTileBytes + ks * tc::kSlabBytes) >> 4),
                                          bd + (uint64_t)((ks * kVtSlabBytes) >> 4), idesc, ks > 0);
         }
         if (lane == 0 && sh->trace && n.b < 64) sh->trace[320 + n.b] = clock64();
 #pragma unroll
         for (int m = 0; m < 3; ++m)
-            if (m < mtiles) umma::commit_elect(&sh->d_full[(n.u + m) % kVtUnits]);
+            if (m < mtiles) umma::commit_elect(&sh->d_full[(n.u + m) % UNITS]);
         umma::commit_elect(&sh->b_empty[bs]);
         if (lane == 0 && sh->trace && n.b < 64) sh->trace[128 + n.b] = clock64();
         n.u += mtiles;
@@ -160,12 +168,12 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB> *sh, uint32_t t
 }
 
 // ---- compute warps: publish a phase (A tiles are complete) ----
-template <int NB>
-__device__ __forceinline__ void vq_tc_publish(VqTcShared<NB> *sh, VqTcCount &n, int nchunks, int mtiles, uint32_t a_addr, int p_nchunks,
+template <int NB, int NT = kComputeThreads, int UNITS>
+__device__ __forceinline__ void vq_tc_publish(VqTcShared<NB, UNITS> *sh, VqTcCount &n, int nchunks, int mtiles, uint32_t a_addr, int p_nchunks,
                                               long long b_off, uint32_t ring_addr, int last, int tid)
 {
     umma::fence_async_smem();                    // generic-proxy writes of the A tiles -> async proxy (tcgen05.mma reads)
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
     if (tid == 0) {
         if (n.go > 0) mbar_wait(&sh->ack, (n.go - 1) & 1u);      // both other roles have read the previous control word
         sh->ctl.nchunks = nchunks; sh->ctl.mtiles = mtiles; sh->ctl.last = last; sh->ctl.a_addr = a_addr;
@@ -175,14 +183,14 @@ __device__ __forceinline__ void vq_tc_publish(VqTcShared<NB> *sh, VqTcCount &n, 
     ++n.go;
 }
 // a frame without any search still tells the other two roles that the frame is over
-template <int NB>
-__device__ __noinline__ void vq_tc_publish_idle(VqTcShared<NB> *sh, int tid)
+template <int NB, int NT = kComputeThreads, int UNITS>
+__device__ FPC_VQ_TC_OUTLINE void vq_tc_publish_idle(VqTcShared<NB, UNITS> *sh, int tid)
 {
     VqTcCount n{sh->cnt_go, 0u, 0u, 0u};
-    vq_tc_publish<NB>(sh, n, 0, 0, 0u, 0, 0, 0u, 1, tid);
-    named_bar_sync(1, kComputeThreads);          // every thread has read cnt_go
+    vq_tc_publish<NB, NT, UNITS>(sh, n, 0, 0, 0u, 0, 0, 0u, 1, tid);
+    named_bar_sync(1, NT);          // every thread has read cnt_go
     if (tid == 0) sh->cnt_go = n.go;
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
 }
 
 // Six smallest packed keys of a stream: new t_i = min(t_i, max(t_{i-1}, x)), all from the old values (11 instructions).
@@ -203,22 +211,24 @@ struct Top6 {
 // r < 8 is the (r+1)-th smallest of the row.  A list only kept its six smallest keys, so whatever it dropped is larger
 // than its sixth key: r6[v] = smallest rank of any list's sixth key tells the decision how many of the row's smallest
 // keys are certainly complete (a candidate set that reaches a sixth key may miss a seventh of that list).
-template <int NL>
+// (kHalves = 2: 256 scanning threads, list l = (replica l >> 1, column half l & 1), kept by thread 32 (quarter + 4 half) + lane;
+//  kHalves = 1: 128 scanning threads, list l = replica l, kept by thread `row`.)
+template <int NL, int kHalves = 2>
 __device__ __forceinline__ void vq_tc_rank_list(const unsigned *__restrict__ keys, int P2, int v, int l, unsigned *__restrict__ g8,
                                                 int *__restrict__ exh)
 {
     unsigned mine[6];
     int rank[6] = {0, 0, 0, 0, 0, 0};
     {
-        const int row = (l >> 1) * P2 + v;
-        const unsigned *kp = keys + (32 * (((row >> 5) & 3) + 4 * (l & 1)) + (row & 31)) * 6;
+        const int row = (kHalves == 2 ? (l >> 1) : l) * P2 + v;
+        const unsigned *kp = keys + (kHalves == 2 ? (32 * (((row >> 5) & 3) + 4 * (l & 1)) + (row & 31)) : row) * 6;
 #pragma unroll
         for (int p6 = 0; p6 < 6; ++p6) mine[p6] = kp[p6];
     }
 #pragma unroll
     for (int o = 0; o < NL; ++o) {
-        const int row = (o >> 1) * P2 + v;
-        const unsigned *kp = keys + (32 * (((row >> 5) & 3) + 4 * (o & 1)) + (row & 31)) * 6;
+        const int row = (kHalves == 2 ? (o >> 1) : o) * P2 + v;
+        const unsigned *kp = keys + (kHalves == 2 ? (32 * (((row >> 5) & 3) + 4 * (o & 1)) + (row & 31)) : row) * 6;
 #pragma unroll
         for (int j = 0; j < 6; ++j) {
             const unsigned k = kp[j];
@@ -236,8 +246,8 @@ __device__ __forceinline__ void vq_tc_rank_list(const unsigned *__restrict__ key
 
 // Exact search for the rows the screen could not decide (and for books too small for the screen): the block-wide
 // vq_search_rows (fpc_vq_search.cuh), the reference's arithmetic for every candidate.  Out of line: one copy per dtype.
-template <typename T>
-__device__ __noinline__ void vq_tc_fallback(const PackedVq &bk, const char *__restrict__ cbbase, const int *__restrict__ flist, int nflag, int maxn,
+template <typename T, int NT = kComputeThreads>
+__device__ FPC_VQ_TC_OUTLINE void vq_tc_fallback(const PackedVq &bk, const char *__restrict__ cbbase, const int *__restrict__ flist, int nflag, int maxn,
                                             const float *__restrict__ rs, float *__restrict__ rq, int *__restrict__ idx1, int *__restrict__ idx2,
                                             char *__restrict__ scratch, int scratch_bytes, int tid)
 {
@@ -247,7 +257,7 @@ __device__ __noinline__ void vq_tc_fallback(const PackedVq &bk, const char *__re
     int vbe = (scratch_bytes - (int)vq_fixed_bytes<T>(sb)) / (1024 * (int)sizeof(T));
     vbe = vbe > 8 ? 8 : vbe;
     for (int off = 0; off < nflag; off += sb)
-        vq_search_rows<T, kComputeThreads>(bk, cbbase, flist + off, min(sb, nflag - off), sb, rs, rq, idx1, idx2, scratch, vbe, tid, nullptr);
+        vq_search_rows<T, NT>(bk, cbbase, flist + off, min(sb, nflag - off), sb, rs, rq, idx1, idx2, scratch, vbe, tid, nullptr);
 }
 
 struct VqTcMem {
@@ -261,17 +271,22 @@ struct VqTcMem {
 };
 __host__ __device__ constexpr int vq_tc_small_bytes(int maxn) { return maxn * (5 * 4 + 5 * 4 + 2 * 4 + 4 + 4 + 4) + 64; }
 
-// Every one of the 256 compute threads calls this with identical arguments.  `last` = this is the last search of the frame.
-template <typename T, int MAXN, int NB>
-__device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__restrict__ cbbase, const int *__restrict__ list, int n,
+// Every one of the NT searching threads (256: two warps per TMEM lane quarter, each scanning one half of a unit's 64
+// columns; 128: one warp per quarter scanning both halves) calls this with identical arguments and tid in [0, NT).
+// `last` = this is the last search of the frame.
+template <typename T, int MAXN, int NB, int NT = kComputeThreads, int UNITS>
+__device__ FPC_VQ_TC_OUTLINE void vq_tc_search(const PackedVq &bk_in, const char *__restrict__ cbbase, const int *__restrict__ list, int n,
                                              const float *__restrict__ rs, float *__restrict__ rq, int *__restrict__ idx1, int *__restrict__ idx2,
-                                             const VqTcMem &mem, VqTcShared<NB> *sh, int last, int tid, long long *dbg)
+                                             const VqTcMem &mem, VqTcShared<NB, UNITS> *sh, int last, int tid, long long *dbg)
 {
     constexpr int MTMAX = (5 * MAXN + 127) / 128;
     const uint32_t tb = sh->tmem_base;
     VqTcCount cnt{sh->cnt_go, sh->cnt_b, sh->cnt_u, 0u};
     static_assert(MAXN <= 64 && MTMAX <= 3, "rows: at most 64 vectors x 5 survivors = 3 tiles");
     const int warp = tid >> 5, lane = tid & 31;
+    static_assert(NT == 256 || NT == 128, "searching threads");
+    constexpr int kHalves = NT / 128;           // warps per lane quarter
+    constexpr int kLoads = 2 / kHalves;         // 32-column loads a warp makes per unit
     const int q = warp & 3, hh = warp >> 2;
     PackedVq bk;
     {
@@ -308,7 +323,7 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
         flag[tid] = 0;
         reinterpret_cast<int *>(mem.part + 256 * 24 + MAXN * 32)[tid] = 8;      // stage 0: smallest rank of a list's sixth key
     }
-    named_bar_sync(1, kComputeThreads);
+    named_bar_sync(1, NT);
     FPC_VQT(2);
 
     if (two) {
@@ -337,28 +352,34 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
                 tc::store_row<true>(mem.a, rho * P2 + v, xs, one, one, one, o0, o1, o2);
             }
         }
-        vq_tc_publish<NB>(sh, cnt, nchunks, 1, smem_u32(mem.a), 2 * nchunks, bk.off_b[0] + (long long)(blockIdx.x % kWeightReplicas) * bk.b_rep_stride, smem_u32(mem.bring), 0, tid);
+        vq_tc_publish<NB, NT, UNITS>(sh, cnt, nchunks, 1, smem_u32(mem.a), 2 * nchunks, bk.off_b[0] + (long long)(blockIdx.x % kWeightReplicas) * bk.b_rep_stride, smem_u32(mem.bring), 0, tid);
         // scan: quarter q belongs to replica (32 q) / P2 and takes the chunks c = replica (mod rep)
         const int my_rep = (32 * q) / P2;
         Top6 tk;
         tk.reset();
         for (int c = 0; c < nchunks; ++c, ++cnt.u) {
-            const int ds = (int)(cnt.u % kVtUnits);
+            const int ds = (int)(cnt.u % UNITS);
             const long long tw0 = dbg ? clock64() : 0;
-            mbar_wait(&sh->d_full[ds], (cnt.u / kVtUnits) & 1u);
+            mbar_wait(&sh->d_full[ds], (cnt.u / UNITS) & 1u);
             if (dbg) dbg[c == 0 ? 8 : 9] += clock64() - tw0;
 
             umma::fence_after_sync();
             if (c % rep == my_rep && (32 * q) % P2 < n) {
-                uint32_t v[32];
-                tc::tmem_ld32(tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 64 + 32 * hh), v);
-                tc::tmem_ld_wait(v);
-                umma::fence_before_sync();
-                __syncwarp();
-                if (lane == 0) mbar_arrive(&sh->d_empty[ds]);
-                const unsigned cbase = (unsigned)(64 * c + 32 * hh);
 #pragma unroll
-                for (int j = 0; j < 32; ++j) tk.insert(__uint_as_float((v[j] & 0xfffffc00u) | (cbase + j)));
+                for (int ld = 0; ld < kLoads; ++ld) {
+                    const int h2 = kLoads == 1 ? hh : ld;
+                    uint32_t v[32];
+                    tc::tmem_ld32(tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 64 + 32 * h2), v);
+                    tc::tmem_ld_wait(v);
+                    if (ld == kLoads - 1) {
+                        umma::fence_before_sync();
+                        __syncwarp();
+                        if (lane == 0) mbar_arrive(&sh->d_empty[ds]);
+                    }
+                    const unsigned cbase = (unsigned)(64 * c + 32 * h2);
+#pragma unroll
+                    for (int j = 0; j < 32; ++j) tk.insert(__uint_as_float((v[j] & 0xfffffc00u) | (cbase + j)));
+                }
             } else {
                 umma::fence_before_sync();
                 __syncwarp();
@@ -369,21 +390,21 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
             float *kp = reinterpret_cast<float *>(mem.part) + tid * 6;
             kp[0] = tk.t0; kp[1] = tk.t1; kp[2] = tk.t2; kp[3] = tk.t3; kp[4] = tk.t4; kp[5] = tk.t5;
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         FPC_VQT(3);
         // ---- the eight smallest keys of every vector: thread (vector v, list l) ranks the six keys of list l among all
         //      2 rep sorted lists of the row (the keys are distinct: they carry the codeword index); l is uniform per warp ----
         unsigned *g8 = reinterpret_cast<unsigned *>(mem.part + 256 * 24);        // [n][8]
         int *exh = reinterpret_cast<int *>(g8 + MAXN * 8);                        // [n]
         {
-            const int v = tid & (P2 - 1), l = tid / P2;                           // 2 rep = 256 / P2 lists
+            const int v = tid & (P2 - 1), l = tid / P2;                           // kHalves rep = NT / P2 lists
             if (v < n) {
                 const unsigned *keys = reinterpret_cast<const unsigned *>(mem.part);
-                if (rep == 2) vq_tc_rank_list<4>(keys, P2, v, l, g8, exh);
-                else vq_tc_rank_list<8>(keys, P2, v, l, g8, exh);
+                if (rep == 2) vq_tc_rank_list<2 * kHalves, kHalves>(keys, P2, v, l, g8, exh);
+                else vq_tc_rank_list<4 * kHalves, kHalves>(keys, P2, v, l, g8, exh);
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         if (tid < n) {
             const int v = tid;
             unsigned g[8];
@@ -412,11 +433,11 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
             exh[v] = rerank ? 2 + nc : 0;
             if (!rerank && (!ok || bad)) flag[v] = 1;
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         // ---- near-ties: lane r < nc evaluates candidate r with the reference's exact arithmetic (dist17<T>), then the five
         //      smallest (distance, index) pairs in order; rare, a warp per vector ----
 #pragma unroll 1
-        for (int v = warp; v < n; v += kComputeThreads / 32) {
+        for (int v = warp; v < n; v += NT / 32) {
             const int st = exh[v];
             if (st < 2) continue;
             const int nc = st - 2;
@@ -446,7 +467,7 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
             }
             if (lane == 0 && !good) flag[v] = 1;
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         FPC_VQT(4);
     }
 
@@ -457,7 +478,7 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
         const int nrows = n * ns;
         const int mtiles = (nrows + 127) >> 7;
         const T *cbr0 = reinterpret_cast<const T *>(cbbase + bk.off_r[0]);
-        for (int r = tid; r < nrows; r += kComputeThreads) {
+        for (int r = tid; r < nrows; r += NT) {
             const int v = two ? r / kSurv : r, s = two ? r - v * kSurv : 0;
             const float *xr = rs + list[v] * kLdR + 4;
             float xs[kDim];
@@ -485,7 +506,7 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
             const __half one = __float2half_rn(1.0f);
             tc::store_row<true>(mem.a + (size_t)(r >> 7) * tc::kTileBytes, r & 127, xs, one, one, one);
         }
-        vq_tc_publish<NB>(sh, cnt, nchunks, mtiles, smem_u32(mem.a), two ? 0 : nchunks,
+        vq_tc_publish<NB, NT, UNITS>(sh, cnt, nchunks, mtiles, smem_u32(mem.a), two ? 0 : nchunks,
                           bk.off_b[sc1] + (long long)(blockIdx.x % kWeightReplicas) * bk.b_rep_stride, smem_u32(mem.bring), last, tid);
         tc::Scan sc[MTMAX];
 #pragma unroll
@@ -494,19 +515,24 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
 #pragma unroll
             for (int m = 0; m < MTMAX; ++m) {
                 if (m < mtiles) {
-                    const int ds = (int)(cnt.u % kVtUnits);
+                    const int ds = (int)(cnt.u % UNITS);
                     const long long tw0 = dbg ? clock64() : 0;
-                    mbar_wait(&sh->d_full[ds], (cnt.u / kVtUnits) & 1u);
+                    mbar_wait(&sh->d_full[ds], (cnt.u / UNITS) & 1u);
                     (void)tw0;
                     umma::fence_after_sync();
                     if (128 * m + 32 * q < nrows) {
-                        uint32_t v[32];
-                        tc::tmem_ld32(tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 64 + 32 * hh), v);
-                        tc::tmem_ld_wait(v);
-                        umma::fence_before_sync();
-                        __syncwarp();
-                        if (lane == 0) mbar_arrive(&sh->d_empty[ds]);
-                        sc[m].feed(v, 2 * c);
+#pragma unroll
+                        for (int ld = 0; ld < kLoads; ++ld) {
+                            uint32_t v[32];
+                            tc::tmem_ld32(tb + ((uint32_t)(32 * q) << 16) + (uint32_t)(ds * 64 + 32 * (kLoads == 1 ? hh : ld)), v);
+                            tc::tmem_ld_wait(v);
+                            if (ld == kLoads - 1) {
+                                umma::fence_before_sync();
+                                __syncwarp();
+                                if (lane == 0) mbar_arrive(&sh->d_empty[ds]);
+                            }
+                            sc[m].feed(v, kLoads == 1 ? 2 * c : 4 * c + 2 * ld);     // group ids: per half / over all 64 columns
+                        }
                     } else {
                         umma::fence_before_sync();
                         __syncwarp();
@@ -524,12 +550,17 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
                     float best, second;
                     int jb;
                     sc[m].finish(best, second, jb);
-                    const int col = 64 * (sc[m].ga >> 1) + 32 * hh + 16 * (sc[m].ga & 1) + jb;
-                    pp[(m * 128 + 32 * q + lane) * 2 + hh] = make_float4(best, second, __int_as_float(col), 0.0f);
+                    if (kLoads == 1) {
+                        const int col = 64 * (sc[m].ga >> 1) + 32 * hh + 16 * (sc[m].ga & 1) + jb;
+                        pp[(m * 128 + 32 * q + lane) * 2 + hh] = make_float4(best, second, __int_as_float(col), 0.0f);
+                    } else {
+                        pp[(m * 128 + 32 * q + lane) * 2] = make_float4(best, second, __int_as_float(16 * sc[m].ga + jb), 0.0f);
+                        pp[(m * 128 + 32 * q + lane) * 2 + 1] = make_float4(inf, inf, __int_as_float(0), 0.0f);
+                    }
                 }
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         FPC_VQT(5);
         if (tid < n && !flag[tid]) {
             const int v = tid;
@@ -614,14 +645,14 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
                 flag[v] = 1;
             }
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
     }
 
     // ---- quantised vectors of the decided rows: csum = 0; csum += CB[i][index[i,0]]  (vq_func.py:127-129) ----
     {
         const T *cbr0 = reinterpret_cast<const T *>(cbbase + bk.off_r[0]);
         const T *cbr1 = reinterpret_cast<const T *>(cbbase + bk.off_r[1]);
-        for (int e = tid; e < n * kDim; e += kComputeThreads) {
+        for (int e = tid; e < n * kDim; e += NT) {
             const int v = e / kDim, d = e - v * kDim;
             if (!flag[v]) {
                 const int row = list[v];
@@ -641,7 +672,7 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
             }
             if (lane == 0) cntw[0] = nf2;
         }
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
     }
     const int nflag = cntw[0];
     if (tid == 0) { sh->cnt_go = cnt.go; sh->cnt_u = cnt.u; }      // (read again only after further barriers)
@@ -650,11 +681,11 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
     if (nflag > 0) {
         // the exact CUDA-core search for the undecided rows; it reuses the scratch, so the row list moves out of it
         const int mine = tid < nflag ? flist[tid] : 0;
-        named_bar_sync(1, kComputeThreads);
+        named_bar_sync(1, NT);
         int *tail = mem.tail;
         if (tid < nflag) tail[tid] = mine;
-        named_bar_sync(1, kComputeThreads);
-        vq_tc_fallback<T>(bk, cbbase, tail, nflag, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
+        named_bar_sync(1, NT);
+        vq_tc_fallback<T, NT>(bk, cbbase, tail, nflag, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
         FPC_VQT(7);
     }
 #undef FPC_VQT
@@ -663,17 +694,17 @@ __device__ __noinline__ void vq_tc_search(const PackedVq &bk_in, const char *__r
 // One VQ search of the fused kernels (one book, the rows of `list`): tensor-core screen when the book has at least
 // 64 entries, the CUDA-core search otherwise.  Returns true if a phase was published (the caller owes the other roles
 // one publication with last = 1 per frame).
-template <int MAXN, int NB>
+template <int MAXN, int NB, int NT = kComputeThreads, int UNITS>
 __device__ __forceinline__ bool vq_tc_dispatch(const PackedVq &bk, const char *cbbase, const int *list, int n, const float *rs, float *rq,
-                                               int *idx1, int *idx2, const VqTcMem &mem, VqTcShared<NB> *sh, int last, int tid, long long *dbg)
+                                               int *idx1, int *idx2, const VqTcMem &mem, VqTcShared<NB, UNITS> *sh, int last, int tid, long long *dbg)
 {
     if (bk.K >= 64) {
-        if (bk.dtype == FPC_F32) vq_tc_search<float, MAXN, NB>(bk, cbbase, list, n, rs, rq, idx1, idx2, mem, sh, last, tid, dbg);
-        else vq_tc_search<double, MAXN, NB>(bk, cbbase, list, n, rs, rq, idx1, idx2, mem, sh, last, tid, dbg);
+        if (bk.dtype == FPC_F32) vq_tc_search<float, MAXN, NB, NT, UNITS>(bk, cbbase, list, n, rs, rq, idx1, idx2, mem, sh, last, tid, dbg);
+        else vq_tc_search<double, MAXN, NB, NT, UNITS>(bk, cbbase, list, n, rs, rq, idx1, idx2, mem, sh, last, tid, dbg);
         return true;
     }
-    if (bk.dtype == FPC_F32) vq_tc_fallback<float>(bk, cbbase, list, n, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
-    else vq_tc_fallback<double>(bk, cbbase, list, n, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
+    if (bk.dtype == FPC_F32) vq_tc_fallback<float, NT>(bk, cbbase, list, n, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
+    else vq_tc_fallback<double, NT>(bk, cbbase, list, n, MAXN, rs, rq, idx1, idx2, mem.scratch, mem.scratch_bytes, tid);
     return false;
 }
 

@@ -22,7 +22,7 @@
  *     (stable sorted() / argmin).
  *   - The predictor (torch.nn.GRU / Linear on MKL) has no documented summation order,
  *     so the oracle fixes one: every dot product is a single fused-multiply-add chain
- *     in ascending k, seeded with the bias, input part first then hidden part; sigmoid
+ *     in ascending k, seeded with the bias, hidden part first then input part; sigmoid
  *     and tanh are the polynomial forms below (only IEEE add/mul/fma/div, so the CUDA
  *     kernel can reproduce them exactly).  The oracle-vs-reference difference this
  *     introduces (~1e-7) is measured against golden vectors produced by the real
@@ -120,15 +120,17 @@ static void orc_gru_cell(int in_dim, int H, const float *w_ih, const float *w_hh
         float az = b_ih[H + j] + b_hh[H + j];
         float ani = b_ih[2 * H + j];
         float anh = b_hh[2 * H + j];
-        for (int k = 0; k < in_dim; ++k) {
-            ar = fmaf(wir[k], x[k], ar);
-            az = fmaf(wiz[k], x[k], az);
-            ani = fmaf(win[k], x[k], ani);
-        }
+        /* hidden part first: it does not depend on the frame that is fed back, so the CUDA kernel can run it for
+         * frame t+1 while frame t is still in the quantiser */
         for (int k = 0; k < H; ++k) {
             ar = fmaf(whr[k], h[k], ar);
             az = fmaf(whz[k], h[k], az);
             anh = fmaf(whn[k], h[k], anh);
+        }
+        for (int k = 0; k < in_dim; ++k) {
+            ar = fmaf(wir[k], x[k], ar);
+            az = fmaf(wiz[k], x[k], az);
+            ani = fmaf(win[k], x[k], ani);
         }
         float r = orc_sigmoidf(ar);
         float z = orc_sigmoidf(az);

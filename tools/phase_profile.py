@@ -17,14 +17,14 @@ if bf16:
 d = tempfile.mkdtemp(); cfg = S.save_codebooks(S.make_codebooks(0), d)
 base = S.make_features(min(U, 256), L)
 feat = torch.from_numpy(np.tile(base, ((U + len(base) - 1) // len(base), 1, 1))[:U]).cuda()
-buf = torch.zeros(16 * 1024, dtype=torch.int64, device="cuda")     # one row of 16 counters per CTA
+buf = torch.zeros(16 * 1024, dtype=torch.int64, device="cuda")     # one row of 32 counters per CTA
 with torch.no_grad():
     m.encode_device(cfg, feat, None, l1, l2); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
     e0.record(); res = m.encode_device(cfg, feat, None, l1, l2); e1.record(); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(None)
-c = buf.cpu().numpy().astype(np.float64)[:8192].reshape(-1, 16)
+c = buf.cpu().numpy().astype(np.float64)[:8192].reshape(-1, 32)
 c = c[c[:, 5] > 0]
 fr = c[:, 5:6]
 names = ["gru", "fc+residual", "thresholds+scalar", "vq", "feedback/out"]
@@ -38,6 +38,9 @@ print("vq rows %d, sent to the exact search %d (%.2f %%)" % (c[:, 6].sum(), c[:,
 for i, n_ in enumerate(["margins", "stage-0 screen", "stage-0 select", "last-stage screen", "merge+gather", "exact fallback"]):
     print("     vq/%-18s mean %8.0f cycles/frame" % (n_, (c[:, 8 + i] / fr[:, 0]).mean()))
 print("     vq/wait for MMA units: stage 0 %8.0f, last stage %8.0f cycles/frame (thread 0)" % ((c[:, 14] / fr[:, 0]).mean(), (c[:, 15] / fr[:, 0]).mean()))
+if c[:, 16].sum() > 0 or c[:, 17].sum() > 0:
+    print("  fp32 roles: GEMM warps busy %8.0f, waiting for the tail %8.0f; tail waiting for h2 %8.0f cycles/frame" % (
+        (c[:, 0] / fr[:, 0]).mean(), (c[:, 16] / fr[:, 0]).mean(), (c[:, 17] / fr[:, 0]).mean()))
 print("above-threshold fractions: c0 %.3f  c1..17 %.3f" % (res.ind1.mean().item(), res.ind2.mean().item()))
 
 if bf16:

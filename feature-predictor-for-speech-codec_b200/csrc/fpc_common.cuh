@@ -183,6 +183,12 @@ __device__ __forceinline__ void mbar_wait(uint64_t *bar, uint32_t parity)
         if (clock64() - t0 > 16000000000LL) __trap();
     }
 }
+// (Round 2, measured and rejected: the same loop around try_wait with a long suspend-time hint, so that waiting warps
+// park instead of polling -- in the role-split fp32 kernel the polling loops are 40 % of all executed warp-instructions.
+// It did not make the gate GEMM faster, and on the barriers of the bulk-copy weight ring it produced wrong results under
+// full load: weights of a neighbouring group were read now and then (results differed by ~1e-5 between tiles holding the
+// same utterances), while the same build with the plain loop on those two barriers was bit-exact.  Not understood; the
+// hint is only used where it has always been, on the `go` barrier of the VQ helper roles, fpc_vq_tc.cuh.)
 // global -> shared bulk copy, completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(void *smem_dst, const void *gsrc, uint32_t bytes, uint64_t *bar)
 {

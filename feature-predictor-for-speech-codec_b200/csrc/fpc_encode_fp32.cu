@@ -28,6 +28,8 @@
 // GEMM warps and tail meet at two mbarriers per frame (x_ready, h2_ready); h2 is double-buffered, h1 is updated in place.
 // A launch covers the frame range [f0, f1) of every utterance; with EncodeParams::state the recurrent state of each
 // tile is carried from one launch to the next (fpc_encode_host cuts a batch along time that way).
+#include <cstdlib>
+
 #include "fpc_common.cuh"
 #include "fpc_math.cuh"
 #include "fpc_vq.cuh"
@@ -38,7 +40,11 @@
 
 namespace fpc {
 
-constexpr int kStages = 4;             // weight ring depth
+#ifndef FPC_STAGES
+#define FPC_STAGES 4
+#endif
+constexpr int kStages = FPC_STAGES;             // weight ring depth
+static_assert(kStages <= 8, "h1 is updated in place: a GEMM warp may run at most kStages groups ahead of the slowest");
 constexpr int kTailThreads = 128;
 constexpr int kThreads = kComputeThreads + kTailThreads + 128;   // 2 GEMM warpgroups + tail warpgroup + helper warpgroup
 constexpr int kTailWarp0 = kComputeThreads / 32;                 // 8
@@ -160,15 +166,21 @@ template <> struct TmIo<16> {
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t ta, const uint32_t *r)
 {
     static_assert(N >= 0 && N % 2 == 0, "even column counts");
+#ifndef FPC_TMEM_MAX8
     if constexpr (N >= 16) { TmIo<16>::st(ta, r); tmem_st_n<N - 16>(ta + 16, r + 16); }
-    else if constexpr (N >= 8) { TmIo<8>::st(ta, r); tmem_st_n<N - 8>(ta + 8, r + 8); }
+    else
+#endif
+    if constexpr (N >= 8) { TmIo<8>::st(ta, r); tmem_st_n<N - 8>(ta + 8, r + 8); }
     else if constexpr (N >= 4) { TmIo<4>::st(ta, r); tmem_st_n<N - 4>(ta + 4, r + 4); }
     else if constexpr (N >= 2) { TmIo<2>::st(ta, r); }
 }
 template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t ta, uint32_t *r)
 {
+#ifndef FPC_TMEM_MAX8
     if constexpr (N >= 16) { TmIo<16>::ld(ta, r); tmem_ld_n<N - 16>(ta + 16, r + 16); }
-    else if constexpr (N >= 8) { TmIo<8>::ld(ta, r); tmem_ld_n<N - 8>(ta + 8, r + 8); }
+    else
+#endif
+    if constexpr (N >= 8) { TmIo<8>::ld(ta, r); tmem_ld_n<N - 8>(ta + 8, r + 8); }
     else if constexpr (N >= 4) { TmIo<4>::ld(ta, r); tmem_ld_n<N - 4>(ta + 4, r + 4); }
     else if constexpr (N >= 2) { TmIo<2>::ld(ta, r); }
 }
@@ -194,7 +206,7 @@ template <int N> __device__ __forceinline__ void tmem_wait_ld(uint32_t (&a)[N], 
 template <int TU>
 __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], float2 (&an)[TU], int ng,
                                           const float *__restrict__ arow, int lda, const float4 *__restrict__ ring,
-                                          uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
+                                          uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane, uint32_t zmask)
 {
     constexpr int NP = kGk / 2;      // k-pairs per group
     for (int g = 0; g < ng; ++g) {
@@ -232,8 +244,18 @@ __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], fl
         }
 #endif
 #ifndef FPC_DEBUG_NO_STREAM
+        // The stage may be refilled as soon as all eight warps have arrived, so every weight load of this group must have
+        // RETURNED before the arrive -- not merely have been issued.  ptxas orders the arrive against the other memory
+        // operations only: with TU = 8 it sat directly behind the last LDS.128 of the group, 60 FFMA2 ahead of where the
+        // source has it, and under full load a stage was now and then overwritten under a load in flight (weights of
+        // group g + 4 instead of g: results off by ~1e-4 in one row group of a tile, a few times per launch).  The
+        // barrier address is therefore made to depend on what was loaded, through a mask that is zero at run time
+        // only (a constant zero is folded away and the dependence with it).
+        // (Through the accumulators of the last row rather than the weight registers themselves: every LDS.128 of the group
+        // feeds them, and the arrive then sits behind the FFMA2s instead of stalling the warp on the load latency.)
+        uint32_t dep = (__float_as_uint(ar[TU - 1].x) | __float_as_uint(az[TU - 1].x) | __float_as_uint(an[TU - 1].x)) & zmask;
         __syncwarp();
-        if (lane == 0) mbar_arrive(&empty[pp.s]);
+        if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(&empty[pp.s]) + dep));
 #endif
         pp.advance();
     }
@@ -242,7 +264,8 @@ __device__ __forceinline__ void gemm_part(float2 (&ar)[TU], float2 (&az)[TU], fl
 // hidden part of one GRU 1 pass (128 hidden units): bias + W_hh h1 for r, z, n_h -> parked in tensor memory
 template <int TU>
 __device__ __forceinline__ void gru1_hidden_pass(const float *__restrict__ hrow, const float *__restrict__ bias, uint32_t tpark,
-                                                 const float4 *__restrict__ ring, uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
+                                                 const float4 *__restrict__ ring, uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane,
+                                                 uint32_t zmask)
 {
     float2 ar[TU], az[TU], anh[TU];
     const float2 br = *reinterpret_cast<const float2 *>(bias + 0 * 128 + 2 * ug);
@@ -250,7 +273,7 @@ __device__ __forceinline__ void gru1_hidden_pass(const float *__restrict__ hrow,
     const float2 bh = *reinterpret_cast<const float2 *>(bias + 3 * 128 + 2 * ug);
 #pragma unroll
     for (int i = 0; i < TU; ++i) { ar[i] = br; az[i] = bz; anh[i] = bh; }
-    gemm_part<TU>(ar, az, anh, kG1h, hrow, kLd1, ring, full, empty, pp, ug, lane);
+    gemm_part<TU>(ar, az, anh, kG1h, hrow, kLd1, ring, full, empty, pp, ug, lane, zmask);
     uint32_t v[3][2 * TU];
 #pragma unroll
     for (int i = 0; i < TU; ++i) {
@@ -266,7 +289,7 @@ __device__ __forceinline__ void gru1_hidden_pass(const float *__restrict__ hrow,
 template <int TU>
 __device__ __forceinline__ void gru1_input_pass(const float *__restrict__ xrow, const float *__restrict__ bias, uint32_t tpark,
                                                 float *__restrict__ hown, const float4 *__restrict__ ring, uint64_t *full, uint64_t *empty,
-                                                Pipe &pp, int ug, int lane)
+                                                Pipe &pp, int ug, int lane, uint32_t zmask)
 {
     uint32_t vr[2 * TU], vz[2 * TU], vh[2 * TU];
     tmem_ld_n<2 * TU>(tpark, vr);
@@ -281,7 +304,7 @@ __device__ __forceinline__ void gru1_input_pass(const float *__restrict__ xrow, 
         az[i] = make_float2(__uint_as_float(vz[2 * i]), __uint_as_float(vz[2 * i + 1]));
         ani[i] = bi;
     }
-    gemm_part<TU>(ar, az, ani, kG1x, xrow, kLdX, ring, full, empty, pp, ug, lane);
+    gemm_part<TU>(ar, az, ani, kG1x, xrow, kLdX, ring, full, empty, pp, ug, lane, zmask);
 #pragma unroll
     for (int i = 0; i < TU; ++i) {
         float2 *hp = reinterpret_cast<float2 *>(hown + (size_t)(4 * i) * kLd1);
@@ -297,7 +320,7 @@ __device__ __forceinline__ void gru1_input_pass(const float *__restrict__ xrow, 
 template <int TU>
 __device__ __forceinline__ void gru2_pass(const float *__restrict__ xrow, const float *__restrict__ hrow, const float *__restrict__ hold,
                                           float *__restrict__ hnew, const float *__restrict__ bias, const float4 *__restrict__ ring,
-                                          uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane)
+                                          uint64_t *full, uint64_t *empty, Pipe &pp, int ug, int lane, uint32_t zmask)
 {
     float2 ar[TU], az[TU], ani[TU], anh[TU];
     const float2 br = *reinterpret_cast<const float2 *>(bias + 0 * 128 + 2 * ug);
@@ -306,8 +329,8 @@ __device__ __forceinline__ void gru2_pass(const float *__restrict__ xrow, const 
     const float2 bh = *reinterpret_cast<const float2 *>(bias + 3 * 128 + 2 * ug);
 #pragma unroll
     for (int i = 0; i < TU; ++i) { ar[i] = br; az[i] = bz; ani[i] = bi; anh[i] = bh; }
-    gemm_part<TU>(ar, az, anh, kG2h, hrow, kLd2, ring, full, empty, pp, ug, lane);
-    gemm_part<TU>(ar, az, ani, kG2x, xrow, kLd1, ring, full, empty, pp, ug, lane);
+    gemm_part<TU>(ar, az, anh, kG2h, hrow, kLd2, ring, full, empty, pp, ug, lane, zmask);
+    gemm_part<TU>(ar, az, ani, kG2x, xrow, kLd1, ring, full, empty, pp, ug, lane, zmask);
 #pragma unroll
     for (int i = 0; i < TU; ++i) {
         const float2 ho = *reinterpret_cast<const float2 *>(hold + (size_t)(4 * i) * kLd2);
@@ -684,7 +707,7 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
                 named_bar_sync(1, kTailThreads);
                 if (carry && fr + 1 == P.f1)
                     for (int i = ttid; i < MT * kLdX; i += kTailThreads) carry[S::kStateFloats + i] = xin[i];
-                if (ttid == 0) mbar_arrive(x_ready);
+                if (ttid == 0 && fr + 1 < P.f1) mbar_arrive(x_ready);       // (the next tile's set-up arrives for the last frame)
                 FPC_PHASE(kPhOut);
                 if (prof) pt[kPhFrames] += 1;
             }
@@ -712,10 +735,15 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     }
     Pipe pp{0, 0u};
     uint32_t phx = 0;
+    const uint32_t zmask = (uint32_t)(P.f0 >> 31);      // zero (f0 >= 0), but not to the compiler: see gemm_part
     const bool prof = P.prof != nullptr && tid == 0;
     long long t_busy = 0, t_wait = 0;
     for (int tile = blockIdx.x; tile < P.ntiles; tile += gridDim.x) {
         float *carry = P.state ? reinterpret_cast<float *>(P.state) + (size_t)tile * (S::kStateFloats + MT * kLdX) : nullptr;
+        // the tail has set up the first input frame of this tile -- and is therefore done with the previous tile (it read h2)
+        long long t0 = prof ? clock64() : 0;
+        mbar_wait(x_ready, phx); phx ^= 1u;
+        if (prof) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
         if (carry && P.f0 > 0) {       // continue the recurrence where the launch of the previous frame range stopped
             for (int i = tid; i < MT * kLd1; i += kComputeThreads) h1[i] = carry[i];
             for (int i = tid; i < MT * kLd2; i += kComputeThreads) h2buf[0][i] = carry[MT * kLd1 + i];
@@ -725,25 +753,26 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
         }
         named_bar_sync(2, kComputeThreads);
         int cur = 0;
-        long long t0 = prof ? clock64() : 0;
         // hidden part of GRU 1 for the first frame of the range
 #pragma unroll 1
         for (int pass = 0; pass < 3; ++pass)
-            gru1_hidden_pass<TU>(h1 + tg * kLd1, bias + pass * 512, tpark + pass * T::kPassCols, ring, full, empty, pp, ug, lane);
+            gru1_hidden_pass<TU>(h1 + tg * kLd1, bias + pass * 512, tpark + pass * T::kPassCols, ring, full, empty, pp, ug, lane, zmask);
         tmem_wait_st();
         for (int fr = P.f0; fr < P.f1; ++fr) {
-            if (prof) { const long long t = clock64(); t_busy += t - t0; t0 = t; }
-            mbar_wait(x_ready, phx); phx ^= 1u;
-            if (prof) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
+            if (fr > P.f0) {
+                if (prof) { const long long t = clock64(); t_busy += t - t0; t0 = t; }
+                mbar_wait(x_ready, phx); phx ^= 1u;
+                if (prof) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
+            }
             // ---- GRU 1 (wavernn.py:71): input part + gates, three passes of 128 hidden units ----
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass)
                 gru1_input_pass<TU>(xin + tg * kLdX, bias + pass * 512, tpark + pass * T::kPassCols, h1 + tg * kLd1 + pass * 128 + 2 * ug,
-                                    ring, full, empty, pp, ug, lane);
+                                    ring, full, empty, pp, ug, lane, zmask);
             named_bar_sync(2, kComputeThreads);
             // ---- GRU 2 (wavernn.py:76): input is the new h1 ----
             gru2_pass<TU>(h1 + tg * kLd1, h2buf[cur] + tg * kLd2, h2buf[cur] + tg * kLd2 + 2 * ug, h2buf[cur ^ 1] + tg * kLd2 + 2 * ug,
-                          bias + 3 * 512, ring, full, empty, pp, ug, lane);
+                          bias + 3 * 512, ring, full, empty, pp, ug, lane, zmask);
             named_bar_sync(2, kComputeThreads);
             if (tid == 0) mbar_arrive(h2_ready);
             cur ^= 1;
@@ -751,13 +780,11 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
             if (fr + 1 < P.f1) {
 #pragma unroll 1
                 for (int pass = 0; pass < 3; ++pass)
-                    gru1_hidden_pass<TU>(h1 + tg * kLd1, bias + pass * 512, tpark + pass * T::kPassCols, ring, full, empty, pp, ug, lane);
+                    gru1_hidden_pass<TU>(h1 + tg * kLd1, bias + pass * 512, tpark + pass * T::kPassCols, ring, full, empty, pp, ug, lane, zmask);
                 tmem_wait_st();
             }
         }
         if (prof) { const long long t = clock64(); t_busy += t - t0; t0 = t; }
-        mbar_wait(x_ready, phx); phx ^= 1u;          // the tail has finished the last frame (it read h2)
-        if (prof) { const long long t = clock64(); t_wait += t - t0; t0 = t; }
         if (carry) {
             for (int i = tid; i < MT * kLd1; i += kComputeThreads) carry[i] = h1[i];
             for (int i = tid; i < MT * kLd2; i += kComputeThreads) carry[MT * kLd1 + i] = h2buf[cur][i];
@@ -900,6 +927,10 @@ int run_encode_fp32(EncodeParams P, cudaStream_t st, int force_tu)
     if (sms <= 0) return cuda_fail(cudaErrorNoDevice);
     EncodeSegment seg[kMaxSegments];
     int n = 1;
+    if (force_tu == 0) {          // debugging / tests: one tile height for the whole batch (16, 24, 28 or 32)
+        const char *e = getenv("FPC_FP32_TILE");
+        if (e != nullptr && atoi(e) > 0) force_tu = atoi(e) / 4;
+    }
     if (force_tu > 0) seg[0] = EncodeSegment{4 * force_tu, 0, P.B};
     else n = plan_segments(P.B, sms, kHeightsF32, 4, 6.0, seg);
     char *state = reinterpret_cast<char *>(P.state);

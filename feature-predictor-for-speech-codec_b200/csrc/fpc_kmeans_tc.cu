@@ -353,8 +353,14 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
 #pragma unroll
                 for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + row * kDim + d) : 0.0f;
             }
+            // the slot is refilled once every warp has arrived: the loads above must have returned, not just been issued
+            // (see gemm_part in fpc_encode_fp32.cu) -- the barrier address depends on the loaded registers
+            uint32_t dep = 0u;
+#pragma unroll
+            for (int d = 0; d < kDim; ++d) dep |= __float_as_uint(x[d]);
+            dep &= (uint32_t)((unsigned long long)N >> 63);       // zero at run time only (a constant zero is folded away)
             __syncwarp();
-            if (lane == 0) mbar_arrive(&raw_empty[sr]);
+            if (lane == 0) mbar_arrive(reinterpret_cast<uint64_t *>(reinterpret_cast<char *>(&raw_empty[sr]) + dep));
             TCP(2);
             named_bar_sync(1, kTcScan);
             TCP(3);

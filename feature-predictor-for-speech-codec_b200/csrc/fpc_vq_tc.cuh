@@ -542,6 +542,9 @@ __device__ FPC_VQ_TC_OUTLINE void vq_tc_search(const PackedVq &bk_in, const char
                 }
             }
         }
+        // the running counts go back to the control block BEFORE the barriers below: the next search (the other book of
+        // the same frame) reads them on entry, with no barrier of its own in between
+        if (tid == 0) { sh->cnt_go = cnt.go; sh->cnt_u = cnt.u; }
         {
             float4 *pp = reinterpret_cast<float4 *>(mem.part);
 #pragma unroll
@@ -675,7 +678,6 @@ __device__ FPC_VQ_TC_OUTLINE void vq_tc_search(const PackedVq &bk_in, const char
         named_bar_sync(1, NT);
     }
     const int nflag = cntw[0];
-    if (tid == 0) { sh->cnt_go = cnt.go; sh->cnt_u = cnt.u; }      // (read again only after further barriers)
     FPC_VQT(6);
     if (dbg) { dbg[0] += n; dbg[1] += nflag; }
     if (nflag > 0) {

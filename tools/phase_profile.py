@@ -11,6 +11,7 @@ U = int(sys.argv[1]) if len(sys.argv) > 1 else 4096
 L = int(sys.argv[2]) if len(sys.argv) > 2 else 200
 l1, l2 = (float(sys.argv[3]), float(sys.argv[4])) if len(sys.argv) > 4 else (0.09, 0.28)
 bf16 = len(sys.argv) > 5 and sys.argv[5] == "bf16"
+qtz = os.environ.get("FPC_PROF_QTZ", "1") != "0"      # 0: residual mode (no quantiser in the loop)
 m = Wavernn(20, 384, 128, 18).eval(); m.load_state_dict(S.make_state_dict(0)); m = m.cuda()
 if bf16:
     m.precision = N.FPC_PREC_BF16
@@ -19,10 +20,10 @@ base = S.make_features(min(U, 256), L)
 feat = torch.from_numpy(np.tile(base, ((U + len(base) - 1) // len(base), 1, 1))[:U]).cuda()
 buf = torch.zeros(16 * 1024, dtype=torch.int64, device="cuda")     # one row of 32 counters per CTA
 with torch.no_grad():
-    m.encode_device(cfg, feat, None, l1, l2); torch.cuda.synchronize()
+    m.encode_device(cfg, feat, None, l1, l2, qtz=qtz); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(buf.data_ptr())
     e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-    e0.record(); res = m.encode_device(cfg, feat, None, l1, l2); e1.record(); torch.cuda.synchronize()
+    e0.record(); res = m.encode_device(cfg, feat, None, l1, l2, qtz=qtz); e1.record(); torch.cuda.synchronize()
     N.lib().fpc_debug_set_phase_buffer(None)
 c = buf.cpu().numpy().astype(np.float64)[:8192].reshape(-1, 32)
 c = c[c[:, 5] > 0]

@@ -57,8 +57,9 @@ F_VQ_ABOVE, F_VQ_BELOW = 313344.0, 26112.0
 F_SCL_ABOVE, F_SCL_BELOW = 768.0, 48.0
 HBM_BYTES_PER_FRAME = 320.0
 # dram__bytes_read.sum + dram__bytes_write.sum of one fpc::encode_fp32_kernel launch over 4096 x 50 frames, ncu --set full
-# (profiles/r1_final_encode_fp32_ncu_raw.txt): 42.56 MB + 25.26 MB = 331 B per coded frame
-NCU_DRAM_BYTES_PER_FRAME = (42.560000e6 + 25.260800e6) / (4096 * 50)
+# (profiles/r2_encode_fp32_ncu_raw.txt, the role-split kernel of round 2): 41.46 MB + 20.99 MB = 305 B per coded frame
+# (round 1: 331; a launch this short leaves part of its 248 B/frame of output in the 126 MB L2)
+NCU_DRAM_BYTES_PER_FRAME = (41.458688e6 + 20.985600e6) / (4096 * 50)
 
 
 def flops_per_frame(p1, p2):
@@ -447,7 +448,7 @@ def run_ours(args):
             "roofline": {"bound": "fp32", "achieved": achieved, "peak": fp32_peak, "unit": "TFLOP/s",
                          "frac": achieved / fp32_peak, "traffic": NCU_DRAM_BYTES_PER_FRAME * U * L,
                          "traffic_note": "DRAM bytes of this launch scaled from the ncu capture of a 4096 x 50 frame launch "
-                                         "(331 B per frame; algorithmic 320 B per frame)",
+                                         "(305 B per frame, part of the output still in L2; algorithmic 320 B per frame)",
                          "kernel": "fpc::encode_fp32_kernel", "kernel_ms": k_ms,
                          "flop_per_frame": fpf,
                          "peak_source": "148 SM x 128 FFMA lanes x 2 x sm_max_mhz of MEASURED_PEAKS.json (%s); the fp32 "

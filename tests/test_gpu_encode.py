@@ -145,6 +145,30 @@ def test_launch_plan_is_invisible(torch_cuda, model, synth, cbdir):
             assert np.array_equal(big[k][s:s + 300], ref[:min(300, B - s)]), (k, s)
 
 
+@pytest.mark.parametrize("height", [16, 24, 28, 32])
+def test_every_tile_height_under_full_load(torch_cuda, model, oracle, oracle_weights, synth, cbdir, height, monkeypatch):
+    """Every SM busy, two tiles per CTA, one tile height for the whole batch (FPC_FP32_TILE, a test override of the launch
+    plan): all copies of an utterance must carry the same bits whichever tile, row and SM they ran on, and those bits
+    are the oracle's.  Timing-dependent faults only show under load: a weight-ring stage that was released while a load
+    from it was still in flight passed every small test and corrupted one row group of a tile now and then at height 32."""
+    torch = torch_cuda
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, L = 2 * sms * height, 48
+    cbs = synth.make_codebooks(0)
+    cfg = synth.save_codebooks(cbs, os.path.join(cbdir, "load%d" % height))
+    base = synth.make_features(64, L, first_utt=9100)
+    feat = np.ascontiguousarray(np.tile(base, ((B + 63) // 64, 1, 1))[:B])
+    monkeypatch.setenv("FPC_FP32_TILE", str(height))
+    big = run_gpu(torch, model, cfg, feat, 0.25, 2.1)
+    monkeypatch.delenv("FPC_FP32_TILE")
+    ora = oracle.encode(oracle_weights, oracle_codebooks(oracle, cbs), base, 0.25, 2.1)
+    for k in ("idx", "c_in", "r", "r_qtz"):
+        want = ora[k].reshape((64,) + big[k].shape[1:])
+        for s in range(0, B, 64):
+            n = min(64, B - s)
+            assert np.array_equal(big[k][s:s + n], want[:n]), (k, height, s)
+
+
 @pytest.mark.parametrize("B,L,l1,l2,dtype", [
     (1, 1, 0.25, 2.1, np.float32),        # smallest possible call
     (70, 40, 0.25, 2.1, np.float32),      # ragged: not a multiple of any tile height

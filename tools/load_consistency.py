@@ -1,3 +1,9 @@
+#!/usr/bin/env python
+"""Every copy of an utterance in a large batch (all SMs busy) against a small reference run of the same utterances:
+per tile, the first frame and the rows whose residual differs.  Used to find timing-dependent faults of the fp32
+frame-step kernel (a weight-ring stage released under a load in flight showed up as whole row groups of a tile being
+off by ~1e-4 under load only).
+    [FPC_FP32_TILE=16|24|28|32] [QTZ=0] python tools/load_consistency.py <utterances> <frames> <tile height> [l1 l2]"""
 import os, sys, numpy as np, torch, tempfile
 ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 sys.path.insert(0, os.path.join(ROOT, "feature-predictor-for-speech-codec_b200")); sys.path.insert(0, ROOT)

@@ -379,6 +379,44 @@ static bool tc_enabled()
 
 using namespace fpc;
 
+
+// ------------------------------------------------------------------------------------------
+// Column sums of the float32 data IN ROW ORDER, in float32: what np.mean(data, 0) of the reference's vq_train
+// (cb_func.py:34) adds up -- NumPy reduces a C-contiguous (N, 17) array over axis 0 row by row, out[j] += a[i][j], in the
+// array's own dtype.  The sum is inherently serial (17 dependent chains of N additions); one CTA does it: warps 1..7
+// bring the next 256 rows into shared memory while 17 lanes of warp 0 add the current ones.  carry[17] is read at the
+// start and written at the end, so the ranks of a sharded data set continue one another's sums in rank order.
+// ------------------------------------------------------------------------------------------
+namespace fpc {
+constexpr int kSeqRows = 256;
+__global__ void __launch_bounds__(256, 1) kmeans_colsum_seq_kernel(const float *__restrict__ data, long N, float *__restrict__ carry)
+{
+    __shared__ float buf[2][kSeqRows * kDim];
+    const int tid = threadIdx.x;
+    const long nchunks = (N + kSeqRows - 1) / kSeqRows;
+    float acc = tid < kDim ? carry[tid] : 0.0f;
+    auto load = [&](long c, int b, int t0, int nt) {
+        const long first = c * kSeqRows * (long)kDim;
+        const long cnt = min((long)kSeqRows, N - c * kSeqRows) * kDim;
+        for (long i = t0; i < cnt; i += nt) buf[b][i] = __ldg(data + first + i);
+    };
+    if (nchunks > 0) load(0, 0, tid, 256);
+    __syncthreads();
+    for (long c = 0; c < nchunks; ++c) {
+        const int b = (int)(c & 1);
+        if (tid >= 32) {
+            if (c + 1 < nchunks) load(c + 1, b ^ 1, tid - 32, 224);
+        } else if (tid < kDim) {
+            const int rows = (int)min((long)kSeqRows, N - c * kSeqRows);
+#pragma unroll 4
+            for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, buf[b][r * kDim + tid]);
+        }
+        __syncthreads();
+    }
+    if (tid < kDim) carry[tid] = acc;
+}
+}  // namespace fpc
+
 extern "C" {
 
 // replicas of the (K,17)+(K) accumulation table: R K >= 2048 rows, none from that many entries up (the float64
@@ -470,6 +508,14 @@ int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_o
 {
     if (!d_acc || !d_cb_out || K < 1) return FPC_ERR_ARG;
     kmeans_finalize_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_acc, d_acc + (size_t)K * kDim, K, n_total, d_cb_out, d_stats, 1);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+int fpc_kmeans_colsum_f32(const float *d_data, long N, float *d_carry, void *stream)
+{
+    if (N < 0 || (N > 0 && d_data == nullptr) || d_carry == nullptr) return FPC_ERR_ARG;
+    fpc::kmeans_colsum_seq_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_data, N, d_carry);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -67,6 +67,25 @@ def allreduce_kmeans(sums, counts, n_local, group=None, want_total=True):
     return int(round(float(flat[-1].item())))
 
 
+def chain_in_rank_order(step, carry, group=None):
+    """Runs `step()` on rank 0, 1, ... in turn, handing the device tensor `carry` from each rank to all others before
+    the next one starts: a reduction that must visit the shards in order (the float32 row-order sum behind
+    np.mean(data, 0), cb_func.py:34).  Returns the global number of ranks visited."""
+    if not is_distributed(group):
+        step()
+        return 1
+    dist = _dist()
+    me, n = dist.get_rank(group), dist.get_world_size(group)
+    for r in range(n):
+        if r == me:
+            step()
+        t = carry if dist.get_backend(group) == "nccl" else carry.cpu()
+        dist.broadcast(t, src=dist.get_global_rank(group, r) if group is not None else r, group=group)
+        if t is not carry:
+            carry.copy_(t)
+    return n
+
+
 def broadcast_array(arr, group=None, src=0):
     """NumPy array from `src` to every rank (the LBG jitter, cb_func.py:41)."""
     if not is_distributed(group):

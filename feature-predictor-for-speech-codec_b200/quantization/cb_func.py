@@ -170,11 +170,21 @@ def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
     ndims = d.shape[1]
     codebook = np.array(codebook, dtype=np.float64, copy=True)
     draw = (rng.rand if rng is not None else np.random.rand)
-    # codebook[0] = np.mean(data, 0)  (:33): float64 mean of the (global) data
-    col_sum = d.to(torch.float64).sum(0)
-    n_total = fpc_dist.allreduce_kmeans(col_sum, None, d.shape[0], group)
+    # codebook[0] = np.mean(data, 0)  (:33).  The training sets are float32 (train_cb.py:182-187), and NumPy then adds
+    # the rows up one after the other IN float32 and divides in float32: fpc_kmeans_colsum_f32 performs exactly those
+    # additions (serially, one CTA; ranks continue one another's sums in rank order), the division is NumPy's own.
+    n_box = torch.tensor([float(d.shape[0])], dtype=torch.float64, device=dev)
+    n_total = fpc_dist.allreduce_kmeans(n_box, None, d.shape[0], group)
+    carry = torch.zeros(17, dtype=torch.float32, device=dev)
+
+    def _my_rows():
+        with torch.cuda.device(dev):
+            N.check(N.lib().fpc_kmeans_colsum_f32(d.data_ptr(), d.shape[0], carry.data_ptr(), N.current_stream(dev)),
+                    "fpc_kmeans_colsum_f32")
+    fpc_dist.chain_in_rank_order(_my_rows, carry, group)
+    mean0 = np.true_divide(carry.cpu().numpy(), int(n_total))          # float32 / int -> float32, as in np.mean
     cb_full = torch.from_numpy(np.ascontiguousarray(codebook[:nb_entries])).to(dev)
-    cb_full[0] = col_sum / float(n_total)
+    cb_full[0] = torch.from_numpy(mean0.astype(np.float64)).to(dev)
     n_draws = ndims * (nb_entries - 1) * nb_entries // 2
     jitter = None
     if n_draws > 0:

@@ -255,6 +255,11 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
  * call divides, writes the statistics and leaves d_acc ZEROED for the next Lloyd iteration (cb_func.py:71-100 with no
  * memset / pack / unpack launches between the iterations).  n_total <= 0: the sum of the counts. */
 int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_out, double *d_stats, void *stream);
+/* d_carry[17] += column sums of the float32 rows IN ROW ORDER, in float32: the additions np.mean(data, 0) performs for
+ * centroid 0 of vq_train (cb_func.py:34; NumPy reduces a C-contiguous (N,17) float32 array over axis 0 row by row in
+ * float32).  Serial by nature: one CTA, ~8 ns per row.  Ranks of a sharded data set call it in rank order on the carry
+ * of the previous rank. */
+int fpc_kmeans_colsum_f32(const float *d_data, long N, float *d_carry, void *stream);
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 

@@ -95,7 +95,31 @@ def test_kmeans_vs_reference_golden(torch_cuda, oracle):
     # seeded grow-by-one LBG: same jitter stream as the reference's np.random.seed(1234) run
     np.random.seed(int(g["train_seed"]))
     cbt = cb_func.vq_train(g["train_data"], np.zeros((8, 17)), 8)
-    np.testing.assert_allclose(cbt, g["train_cb"], rtol=1e-9, atol=1e-12)
+    # centroid 0 is seeded with NumPy's own float32 row-order mean (fpc_kmeans_colsum_f32): what is left between the two
+    # runs is the order of the float64 additions inside `update` (atomics here, data order in the reference)
+    np.testing.assert_allclose(cbt, g["train_cb"], rtol=CENTROID_RTOL, atol=1e-300)
+
+
+def test_colsum_is_numpy_float32_mean(torch_cuda, synth):
+    """np.mean(data, 0) of float32 data, bit for bit (cb_func.py:34): row-order float32 additions, float32 division."""
+    import fpc_native as N
+    torch = torch_cuda
+    for n in (1, 17, 511, 512, 513, 100003):
+        data = (synth.make_kmeans_data(n, seed=5, n_components=16) * 3.0 + 0.25).astype(np.float32)
+        d = torch.from_numpy(data).cuda()
+        carry = torch.zeros(17, dtype=torch.float32, device="cuda")
+        N.check(N.lib().fpc_kmeans_colsum_f32(d.data_ptr(), n, carry.data_ptr(), N.current_stream(d.device)), "colsum")
+        got = np.true_divide(carry.cpu().numpy(), n)
+        want = np.mean(data, 0)
+        assert got.dtype == want.dtype == np.float32
+        assert np.array_equal(got, want), (n, got, want)
+        # two shards continue one another's sums
+        if n > 1:
+            carry.zero_()
+            h = n // 3
+            N.check(N.lib().fpc_kmeans_colsum_f32(d.data_ptr(), h, carry.data_ptr(), N.current_stream(d.device)), "colsum")
+            N.check(N.lib().fpc_kmeans_colsum_f32(d[h:].data_ptr(), n - h, carry.data_ptr(), N.current_stream(d.device)), "colsum")
+            assert np.array_equal(np.true_divide(carry.cpu().numpy(), n), want)
 
 
 @pytest.mark.parametrize("N,K", [(1, 1), (31, 1), (5000, 7), (20000, 33), (100003, 512), (60000, 1024)])

@@ -367,12 +367,8 @@ constexpr int kTcMinK = 128;      // below this the codebook is a fraction of on
 
 static bool tc_enabled()
 {
-    static int cached = -1;
-    if (cached < 0) {
-        const char *e = getenv("FPC_KMEANS_TC");        // A/B switch for measurements: FPC_KMEANS_TC=0 -> CUDA-core screen
-        cached = (e && e[0] == '0') ? 0 : 1;
-    }
-    return cached != 0;
+    const char *e = getenv("FPC_KMEANS_TC");        // A/B switch for measurements and tests: FPC_KMEANS_TC=0 -> CUDA-core screen
+    return !(e && e[0] == '0');                    // (read on every call: a test flips it between two calls)
 }
 
 }  // namespace fpc

@@ -158,6 +158,23 @@ def test_bf16_full_batch_sample(torch_cuda, model16, synth, cfgdir, oracle, orac
     assert torch.equal(dec, out[0])
 
 
+def test_bf16_every_copy_identical_under_full_load(torch_cuda, model16, synth, cfgdir):
+    """All SMs busy, two 64-utterance tiles per CTA: every copy of an utterance must carry the same bits whichever tile,
+    row and SM it ran on, and the bits it gets in a small batch of its own.  (Timing-dependent faults only show under
+    load; the fp32 kernel had one, tests/test_gpu_encode.py::test_every_tile_height_under_full_load.)"""
+    torch = torch_cuda
+    cfg, _ = cfgdir
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, L = 2 * sms * 64, 40
+    base = synth.make_features(64, L, first_utt=9300)
+    feat = np.ascontiguousarray(np.tile(base, (B // 64, 1, 1)))
+    big = encode(torch, model16, cfg, feat, 0.25, 2.1)
+    small = encode(torch, model16, cfg, base, 0.25, 2.1)
+    for k in ("idx", "c_in", "r_qtz"):
+        for s in range(0, B, 64):
+            assert np.array_equal(big[k][s:s + 64], small[k]), (k, s)
+
+
 @pytest.mark.parametrize("B,L,chunks", [(70, 40, 3), (200, 24, 0), (5, 9, 4)])
 def test_bf16_encode_host_matches_device_path(torch_cuda, model16, synth, cfgdir, B, L, chunks):
     """The host-buffer call cuts the utterances along time and carries the bf16 recurrent state (the B-operand tiles)

@@ -219,3 +219,24 @@ def test_kmeans_tc_adversarial_vs_oracle(torch_cuda, oracle, synth, K):
     new = cb_func.update(data, cb, K, verbose=False)
     want = oracle.kmeans_update(data, cb)
     np.testing.assert_allclose(new, want, rtol=CENTROID_RTOL, atol=1e-300)
+
+
+def test_kmeans_tc_full_load_equals_cuda_core_path(torch_cuda, synth, monkeypatch):
+    """Every SM busy for many tiles: the tensor-core assignment and the CUDA-core one (FPC_KMEANS_TC=0) must give the
+    same index for every vector, the same counts, and sums within the float64 addition-order tolerance.  Timing-
+    dependent faults (a ring slot released under a load in flight) only show at this size."""
+    from quantization import cb_func
+    torch = torch_cuda
+    n, K = 6_000_000, 1024
+    data = torch.from_numpy(synth.make_kmeans_data(n, seed=31, n_components=512)).cuda()
+    g = np.random.Generator(np.random.Philox(key=32))
+    cb = torch.from_numpy(g.standard_normal((K, 17)) * 0.1).cuda()
+    s1, c1, i1 = cb_func.assign_accumulate(data, cb, want_idx=True)
+    s1b, c1b, i1b = cb_func.assign_accumulate(data, cb, want_idx=True)
+    monkeypatch.setenv("FPC_KMEANS_TC", "0")
+    s0, c0, i0 = cb_func.assign_accumulate(data, cb, want_idx=True)
+    monkeypatch.delenv("FPC_KMEANS_TC")
+    assert torch.equal(i1, i0) and torch.equal(i1, i1b)
+    assert torch.equal(c1, c0) and torch.equal(c1, c1b)
+    np.testing.assert_allclose(s1.cpu().numpy(), s0.cpu().numpy(), rtol=1e-11, atol=1e-9)
+    np.testing.assert_allclose(s1.cpu().numpy(), s1b.cpu().numpy(), rtol=1e-11, atol=1e-9)

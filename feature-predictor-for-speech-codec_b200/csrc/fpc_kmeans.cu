@@ -59,7 +59,8 @@ __device__ __forceinline__ float screen17(const float (&x)[kDim], const float *_
     return s;
 }
 
-__device__ __forceinline__ double exact17(const float (&x)[kDim], const double *__restrict__ c)
+template <typename TD>
+__device__ __forceinline__ double exact17(const TD (&x)[kDim], const double *__restrict__ c)
 {
     double xd[kDim], cd[kDim];
 #pragma unroll
@@ -67,9 +68,14 @@ __device__ __forceinline__ double exact17(const float (&x)[kDim], const double *
     return dist17<double>(xd, cd);
 }
 
-// one vector per thread; codebook (float64 + fp32 shadow) resident in shared memory
+// one vector per thread; codebook (float64 + fp32 shadow) resident in shared memory.
+// TD = float: the training vectors as the encoder leaves them.  TD = double: the vectors of a later stage,
+// r = quantize(cb, r) - r, which the reference keeps in float64 (train_cb.py:200).  The screen then runs on the
+// float32 ROUNDING of the vector -- that moves a screened value by at most 2 u ||x|| ||c|| <= u R / 2, far inside the
+// slack of 128 u R -- while the float64 re-evaluation of near-ties and the accumulation use the float64 vector itself.
+template <typename TD>
 __global__ void __launch_bounds__(kKmThreads, 1)
-kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__restrict__ cb, int K,
+kmeans_assign_kernel(const TD *__restrict__ data, long N, const double *__restrict__ cb, int K,
                      double *__restrict__ sums, double *__restrict__ counts, int32_t *__restrict__ idx_out, int R)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -131,7 +137,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
             const long i = i0 + (long)j * kKmThreads;
             float x[kDim];
 #pragma unroll
-            for (int d = 0; d < kDim; ++d) x[d] = i < N ? __ldg(data + i * kDim + d) : 0.0f;
+            for (int d = 0; d < kDim; ++d) x[d] = i < N ? (float)__ldg(data + i * kDim + d) : 0.0f;
             // per-vector screen constants: -2 x (exact), ||x||^2 and the slack A = 128 u (||x|| + Cmax)^2, rounded up
 #pragma unroll
             for (int d = 0; d < kDim; ++d) {
@@ -200,10 +206,14 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
             const bool valid = i < N;
             const float thr = __fadd_ru(m1[j], slack[j]);
             float x[kDim];
+            TD xe[kDim];                  // the vector as given: what the exact distances and the sums use
             const bool need_x = (sums != nullptr) || !(m2[j] > thr);
             if (need_x) {
 #pragma unroll
-                for (int d = 0; d < kDim; ++d) x[d] = valid ? __ldg(data + i * kDim + d) : 0.0f;   // L1/L2 hit
+                for (int d = 0; d < kDim; ++d) {
+                    xe[d] = valid ? __ldg(data + i * kDim + d) : (TD)0;   // L1/L2 hit
+                    x[d] = (float)xe[d];
+                }
             }
             if (!(m2[j] > thr)) {
                 double best = 0.0;
@@ -211,7 +221,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                 for (int k = 0; k < K; ++k) {
                     const float s = screen17(x, cb32, k);
                     if (s <= thr) {
-                        const double d = exact17(x, cb64 + k * kKmLd64);
+                        const double d = exact17<TD>(xe, cb64 + k * kKmLd64);
                         if (!have || d < best) { best = d; bi[j] = k; have = true; }
                     }
                 }
@@ -233,7 +243,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                         const int rep = (int)(((long)blockIdx.x * kKmThreads + threadIdx.x + (long)j * 7) % R);
                         double *s2 = sums + ((size_t)rep * K + b) * kDim;
 #pragma unroll
-                        for (int d = 0; d < kDim; ++d) atomicAdd(s2 + d, (double)x[d]);
+                        for (int d = 0; d < kDim; ++d) atomicAdd(s2 + d, (double)xe[d]);
                         atomicAdd(counts + (size_t)rep * K + b, 1.0);
                     }
                 } else if (K <= 32) {
@@ -247,7 +257,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                         const bool take = (peers >> src) & 1u;
 #pragma unroll
                         for (int d = 0; d < kDim; ++d) {
-                            const double v = __shfl_sync(0xffffffffu, (double)x[d], src);
+                            const double v = __shfl_sync(0xffffffffu, (double)xe[d], src);
                             if (take) acc[d] += v;
                         }
                     }
@@ -258,7 +268,7 @@ kmeans_assign_kernel(const float *__restrict__ data, long N, const double *__res
                     }
                 } else if (valid) {
 #pragma unroll
-                    for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)b * kDim + d, (double)x[d]);
+                    for (int d = 0; d < kDim; ++d) atomicAdd(sums + (size_t)b * kDim + d, (double)xe[d]);
                     atomicAdd(counts + b, 1.0);
                 }
             }
@@ -385,15 +395,17 @@ using namespace fpc;
 // ------------------------------------------------------------------------------------------
 namespace fpc {
 constexpr int kSeqRows = 256;
-__global__ void __launch_bounds__(256, 1) kmeans_colsum_seq_kernel(const float *__restrict__ data, long N, float *__restrict__ carry)
+template <typename TD>
+__global__ void __launch_bounds__(256, 1) kmeans_colsum_seq_kernel(const TD *__restrict__ data, long N, TD *__restrict__ carry)
 {
-    __shared__ float buf[2][kSeqRows * kDim];
+    __shared__ TD buf[2][kSeqRows * kDim / (sizeof(TD) / 4)];
     const int tid = threadIdx.x;
-    const long nchunks = (N + kSeqRows - 1) / kSeqRows;
-    float acc = tid < kDim ? carry[tid] : 0.0f;
+    constexpr int kRows = kSeqRows / (sizeof(TD) / 4);        // rows per chunk: the buffers stay below 48 KB
+    const long nchunks = (N + kRows - 1) / kRows;
+    TD acc = tid < kDim ? carry[tid] : (TD)0;
     auto load = [&](long c, int b, int t0, int nt) {
-        const long first = c * kSeqRows * (long)kDim;
-        const long cnt = min((long)kSeqRows, N - c * kSeqRows) * kDim;
+        const long first = c * kRows * (long)kDim;
+        const long cnt = min((long)kRows, N - c * kRows) * kDim;
         for (long i = t0; i < cnt; i += nt) buf[b][i] = __ldg(data + first + i);
     };
     if (nchunks > 0) load(0, 0, tid, 256);
@@ -403,9 +415,9 @@ __global__ void __launch_bounds__(256, 1) kmeans_colsum_seq_kernel(const float *
         if (tid >= 32) {
             if (c + 1 < nchunks) load(c + 1, b ^ 1, tid - 32, 224);
         } else if (tid < kDim) {
-            const int rows = (int)min((long)kSeqRows, N - c * kSeqRows);
+            const int rows = (int)min((long)kRows, N - c * kRows);
 #pragma unroll 4
-            for (int r = 0; r < rows; ++r) acc = __fadd_rn(acc, buf[b][r * kDim + tid]);
+            for (int r = 0; r < rows; ++r) acc = Rn<TD>::add(acc, buf[b][r * kDim + tid]);
         }
         __syncthreads();
     }
@@ -443,10 +455,14 @@ size_t fpc_kmeans_workspace_bytes(long N, int K)
     return replica_bytes(K) + (K >= kTcMinK ? kmeans_tc_pack_bytes(K) : 0);
 }
 
-int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
-                                 double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
-                                 void *stream)
+}  // extern "C"
+
+template <typename TD>
+static int kmeans_assign_any(const TD *d_data, long N, const double *d_cb, int K, double *d_sums,
+                             double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                             void *stream)
 {
+    constexpr bool kF32 = sizeof(TD) == 4;
     if (N < 0 || K < 1) return FPC_ERR_ARG;
     if (K > FPC_MAX_VQ_ENTRIES) return FPC_ERR_CODEBOOK;
     if (N == 0) return FPC_OK;
@@ -458,7 +474,7 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
     cudaStream_t st = (cudaStream_t)stream;
     const size_t smem = (size_t)K * kKmLd64 * 8 + (size_t)((K + kKmPad - 1) / kKmPad * kKmPad) * kKmLd32 * 4;
     static bool configured[kMaxDevices] = {};
-    { const int rc = ensure_dynamic_smem(kmeans_assign_kernel, (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4)), configured);
+    { const int rc = ensure_dynamic_smem(kmeans_assign_kernel<TD>, (int)((size_t)FPC_MAX_VQ_ENTRIES * (kKmLd64 * 8 + kKmLd32 * 4)), configured);
       if (rc != FPC_OK) return rc; }
     long blocks = (N + (long)kKmThreads * kKmV - 1) / ((long)kKmThreads * kKmV);
     if (blocks > sms) blocks = sms;
@@ -472,13 +488,18 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
         acc_counts = acc_sums + (size_t)R * K * kDim;
         FPC_CUDA_TRY(cudaMemsetAsync(d_workspace, 0, (size_t)R * K * (kDim + 1) * sizeof(double), st));
     }
-    if (K >= kTcMinK && have_ws && tc_enabled() && (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) {
-        // distance screen on the tensor cores (fpc_kmeans_tc.cu); same decisions, same accumulation
-        const int rc = run_kmeans_assign_tc(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R,
-                                            (char *)d_workspace + replica_bytes(K), st);
-        if (rc != FPC_OK) return rc;
-    } else {
-        kmeans_assign_kernel<<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
+    bool on_tc = false;
+    if constexpr (kF32) {
+        if (K >= kTcMinK && have_ws && tc_enabled() && (reinterpret_cast<uintptr_t>(d_data) & 15) == 0) {
+            // distance screen on the tensor cores (fpc_kmeans_tc.cu); same decisions, same accumulation
+            const int rc = run_kmeans_assign_tc(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R,
+                                                (char *)d_workspace + replica_bytes(K), st);
+            if (rc != FPC_OK) return rc;
+            on_tc = true;
+        }
+    }
+    if (!on_tc) {       // (float64 vectors always take the CUDA-core kernel: later training stages only, a13)
+        kmeans_assign_kernel<TD><<<(int)blocks, kKmThreads, smem, st>>>(d_data, N, d_cb, K, acc_sums, acc_counts, d_idx, R);
         FPC_LAUNCH_CHECK();
     }
     if (R > 1) {
@@ -486,6 +507,22 @@ int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb
         FPC_LAUNCH_CHECK();
     }
     return FPC_OK;
+}
+
+extern "C" {
+
+int fpc_kmeans_assign_accumulate(const float *d_data, long N, const double *d_cb, int K, double *d_sums,
+                                 double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                                 void *stream)
+{
+    return kmeans_assign_any<float>(d_data, N, d_cb, K, d_sums, d_counts, d_idx, d_workspace, workspace_bytes, stream);
+}
+
+int fpc_kmeans_assign_accumulate_f64(const double *d_data, long N, const double *d_cb, int K, double *d_sums,
+                                     double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                                     void *stream)
+{
+    return kmeans_assign_any<double>(d_data, N, d_cb, K, d_sums, d_counts, d_idx, d_workspace, workspace_bytes, stream);
 }
 
 int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, double n_total, double *d_cb_out,
@@ -511,7 +548,15 @@ int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_o
 int fpc_kmeans_colsum_f32(const float *d_data, long N, float *d_carry, void *stream)
 {
     if (N < 0 || (N > 0 && d_data == nullptr) || d_carry == nullptr) return FPC_ERR_ARG;
-    fpc::kmeans_colsum_seq_kernel<<<1, 256, 0, (cudaStream_t)stream>>>(d_data, N, d_carry);
+    fpc::kmeans_colsum_seq_kernel<float><<<1, 256, 0, (cudaStream_t)stream>>>(d_data, N, d_carry);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+int fpc_kmeans_colsum_f64(const double *d_data, long N, double *d_carry, void *stream)
+{
+    if (N < 0 || (N > 0 && d_data == nullptr) || d_carry == nullptr) return FPC_ERR_ARG;
+    fpc::kmeans_colsum_seq_kernel<double><<<1, 256, 0, (cudaStream_t)stream>>>(d_data, N, d_carry);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -119,8 +119,10 @@ __global__ void compact_scatter_kernel(const float *__restrict__ src, long n, in
 
 // next[i] = (float)(cb[idx[i]] - (double)data[i])   (float64 codebook minus float32 data promotes, then the k-means
 // input is float32 again)
+// (TO = double keeps the difference as the reference does, train_cb.py:200: float64 codebook minus float32 or float64 data)
+template <typename TD, typename TO>
 __global__ void stage_residual_kernel(const double *__restrict__ cb, int K, const int32_t *__restrict__ idx,
-                                      const float *__restrict__ data, long N, float *__restrict__ next)
+                                      const TD *__restrict__ data, long N, TO *__restrict__ next)
 {
     const long total = N * kDim;
     for (long t = (long)blockIdx.x * blockDim.x + threadIdx.x; t < total; t += (long)gridDim.x * blockDim.x) {
@@ -128,7 +130,7 @@ __global__ void stage_residual_kernel(const double *__restrict__ cb, int K, cons
         const int d = (int)(t - i * kDim);
         const int k = idx[i];
         const double q = (k >= 0 && k < K) ? cb[(size_t)k * kDim + d] : 0.0;
-        next[t] = (float)(q - (double)data[t]);
+        next[t] = (TO)__dsub_rn(q, (double)data[t]);
     }
 }
 
@@ -258,7 +260,21 @@ int fpc_kmeans_stage_residual(const double *d_cb, int K, const int32_t *d_idx, c
     if (N < 0 || K < 1) return FPC_ERR_ARG;
     if (N == 0) return FPC_OK;
     if (!d_cb || !d_idx || !d_data || !d_next) return FPC_ERR_ARG;
-    stage_residual_kernel<<<grid_for(N * kDim, 256), 256, 0, (cudaStream_t)stream>>>(d_cb, K, d_idx, d_data, N, d_next);
+    stage_residual_kernel<float, float><<<grid_for(N * kDim, 256), 256, 0, (cudaStream_t)stream>>>(d_cb, K, d_idx, d_data, N, d_next);
+    FPC_LAUNCH_CHECK();
+    return FPC_OK;
+}
+
+int fpc_kmeans_stage_residual_f64(const double *d_cb, int K, const int32_t *d_idx, const void *d_data, int data_is_f64, long N,
+                                  double *d_next, void *stream)
+{
+    if (N < 0 || K < 1) return FPC_ERR_ARG;
+    if (N == 0) return FPC_OK;
+    if (!d_cb || !d_idx || !d_data || !d_next) return FPC_ERR_ARG;
+    if (data_is_f64)
+        stage_residual_kernel<double, double><<<grid_for(N * kDim, 256), 256, 0, (cudaStream_t)stream>>>(d_cb, K, d_idx, (const double *)d_data, N, d_next);
+    else
+        stage_residual_kernel<float, double><<<grid_for(N * kDim, 256), 256, 0, (cudaStream_t)stream>>>(d_cb, K, d_idx, (const float *)d_data, N, d_next);
     FPC_LAUNCH_CHECK();
     return FPC_OK;
 }

@@ -11,8 +11,9 @@ without the host round trips:
 `training_sets` keeps the rows in order and on the device (C ABI fpc_compact_rows), so the k-means
 kernels consume the residuals where the encoder left them; `train_stages` forms the next stage's
 vectors as `quantize(cb, r) - r` (the reference's sign, :200) with fpc_kmeans_stage_residual.
-The reference's next-stage data is float64 (float64 codebook - float32 residual); here it is rounded
-to float32 because the assign kernel reads float32 vectors -- stated, not hidden.
+The next stage's data is float64 as in the reference (float64 codebook - float32 residual, :200): the k-means entry
+points take float64 vectors (fpc_kmeans_assign_accumulate_f64, fpc_kmeans_colsum_f64) and use them for the exact
+distances, the sums and the seed mean.
 The scalar learner is a plain 1-D Lloyd iteration; parity with the (unpinned, commented-out)
 sklearn KMeans of the reference is not claimed.
 """
@@ -56,19 +57,28 @@ def training_sets(r, r_under, code_dims=17):
     }
 
 
-def stage_residual(codebook, data):
-    """r = quantize(codebook, r) - r on the device (train_cb.py:199-200).  data: CUDA (N,17) float32."""
+def stage_residual(codebook, data, keep_float64=True):
+    """r = quantize(codebook, r) - r on the device (train_cb.py:199-200).  data: CUDA (N,17) float32 or float64.
+    The result is float64 as in the reference; keep_float64=False rounds it to float32 (half the memory, and the next
+    stage then runs on the tensor-core assignment -- a stated deviation from :200)."""
     cb = cb_func._cb_on_device(codebook, data.device)
     _, _, idx = cb_func.assign_accumulate(data, cb, want_idx=True, want_sums=False)
-    nxt = torch.empty_like(data)
     with torch.cuda.device(data.device):
-        N.check(N.lib().fpc_kmeans_stage_residual(cb.data_ptr(), cb.shape[0], idx.data_ptr(), data.data_ptr(), data.shape[0],
-                                                  nxt.data_ptr(), N.current_stream(data.device)), "fpc_kmeans_stage_residual")
+        if keep_float64:
+            nxt = torch.empty(data.shape, dtype=torch.float64, device=data.device)
+            N.check(N.lib().fpc_kmeans_stage_residual_f64(cb.data_ptr(), cb.shape[0], idx.data_ptr(), data.data_ptr(),
+                                                          1 if data.dtype == torch.float64 else 0, data.shape[0], nxt.data_ptr(),
+                                                          N.current_stream(data.device)), "fpc_kmeans_stage_residual_f64")
+        else:
+            d32 = data.to(torch.float32)
+            nxt = torch.empty_like(d32)
+            N.check(N.lib().fpc_kmeans_stage_residual(cb.data_ptr(), cb.shape[0], idx.data_ptr(), d32.data_ptr(), d32.shape[0],
+                                                      nxt.data_ptr(), N.current_stream(data.device)), "fpc_kmeans_stage_residual")
         torch.cuda.current_stream(data.device).synchronize()
     return nxt
 
 
-def train_stages(data, n_entries, codebooks=None, first_batch=True, group=None, rng=None):
+def train_stages(data, n_entries, codebooks=None, first_batch=True, group=None, rng=None, keep_float64=True):
     """train_cb.py:189-211 for one batch of residual vectors: for every stage, `vq_train` (first batch) or ten
     `update` calls (later batches), then the next stage trains on quantize(cb, r) - r.
     Returns the list of (K_i, 17) float64 codebooks."""
@@ -84,7 +94,7 @@ def train_stages(data, n_entries, codebooks=None, first_batch=True, group=None, 
                 cb = cb_func.update(d, cb, K, group=group, verbose=False)
         out.append(cb)
         if i + 1 < len(n_entries):
-            d = stage_residual(cb, d)
+            d = stage_residual(cb, d, keep_float64)
     return out
 
 

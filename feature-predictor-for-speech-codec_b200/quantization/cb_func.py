@@ -28,15 +28,20 @@ def _torch():
 
 
 def _data_on_device(data):
+    """(nb_vectors, 17) training vectors on the device.  float64 input stays float64 -- the data of a later training
+    stage is `quantize(cb, r) - r` in float64 (train_cb.py:200) and NumPy then computes distances, sums and the seed
+    mean in float64; everything else becomes float32, what the encoder's residuals are."""
     torch = _torch()
     N.require_cuda()
     if isinstance(data, torch.Tensor):
         t = data.detach()
         if not t.is_cuda:
             t = t.cuda()
-        t = t.to(torch.float32)
+        if t.dtype != torch.float64:
+            t = t.to(torch.float32)
     else:
-        t = torch.from_numpy(np.ascontiguousarray(np.asarray(data), dtype=np.float32)).cuda()
+        a = np.asarray(data)
+        t = torch.from_numpy(np.ascontiguousarray(a, dtype=np.float64 if a.dtype == np.float64 else np.float32)).cuda()
     if t.dim() != 2 or t.shape[1] != 17:
         raise ValueError("data must be (nb_vectors, 17), got %r" % (tuple(t.shape),))
     return t.contiguous()
@@ -48,6 +53,11 @@ def _cb_on_device(codebook, dev):
     if cb.ndim != 2 or cb.shape[1] != 17:
         raise ValueError("codebook must be (nb_entries, 17), got %r" % (cb.shape,))
     return torch.from_numpy(cb).to(dev)
+
+
+def _assign_fn(data_dev):
+    """The C entry point for the dtype of the vectors (float64: later training stages)."""
+    return N.lib().fpc_kmeans_assign_accumulate_f64 if data_dev.dtype == _torch().float64 else N.lib().fpc_kmeans_assign_accumulate
 
 
 def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
@@ -64,7 +74,7 @@ def assign_accumulate(data_dev, cb_dev, want_idx=False, want_sums=True):
         # scratch: replicated accumulation tables of small codebooks + the operand image of the tensor-core screen
         need = N.lib().fpc_kmeans_workspace_bytes(n, K)
         ws = torch.empty(need, dtype=torch.uint8, device=dev) if need else None
-        N.check(N.lib().fpc_kmeans_assign_accumulate(
+        N.check(_assign_fn(data_dev)(
             data_dev.data_ptr(), n, cb_dev.data_ptr(), K,
             sums.data_ptr() if want_sums else None, counts.data_ptr() if want_sums else None,
             idx.data_ptr() if want_idx else None, ws.data_ptr() if ws is not None else None, need,
@@ -105,7 +115,7 @@ def update_device(data_dev, cb_dev, group=None):
     stats = torch.empty((5,), dtype=torch.float64, device=dev)
     try:
         with torch.cuda.device(dev):
-            N.check(N.lib().fpc_kmeans_assign_accumulate(
+            N.check(_assign_fn(data_dev)(
                 data_dev.data_ptr(), n, cb_dev.data_ptr(), K, acc.data_ptr(), acc.data_ptr() + K * 17 * 8, None,
                 ws.data_ptr(), ws.numel(), N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
             if fpc_dist.is_distributed(group):
@@ -170,19 +180,20 @@ def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
     ndims = d.shape[1]
     codebook = np.array(codebook, dtype=np.float64, copy=True)
     draw = (rng.rand if rng is not None else np.random.rand)
-    # codebook[0] = np.mean(data, 0)  (:33).  The training sets are float32 (train_cb.py:182-187), and NumPy then adds
-    # the rows up one after the other IN float32 and divides in float32: fpc_kmeans_colsum_f32 performs exactly those
-    # additions (serially, one CTA; ranks continue one another's sums in rank order), the division is NumPy's own.
+    # codebook[0] = np.mean(data, 0)  (:33).  The first stage's training set is float32 (train_cb.py:182-187), a later
+    # one float64 (:200), and NumPy adds the rows up one after the other and divides IN THAT dtype: fpc_kmeans_colsum_f32 /
+    # _f64 perform exactly those additions (serially, one CTA; ranks continue one another's sums in rank order), the
+    # division is NumPy's own.
     n_box = torch.tensor([float(d.shape[0])], dtype=torch.float64, device=dev)
     n_total = fpc_dist.allreduce_kmeans(n_box, None, d.shape[0], group)
-    carry = torch.zeros(17, dtype=torch.float32, device=dev)
+    carry = torch.zeros(17, dtype=d.dtype, device=dev)
+    colsum = N.lib().fpc_kmeans_colsum_f64 if d.dtype == torch.float64 else N.lib().fpc_kmeans_colsum_f32
 
     def _my_rows():
         with torch.cuda.device(dev):
-            N.check(N.lib().fpc_kmeans_colsum_f32(d.data_ptr(), d.shape[0], carry.data_ptr(), N.current_stream(dev)),
-                    "fpc_kmeans_colsum_f32")
+            N.check(colsum(d.data_ptr(), d.shape[0], carry.data_ptr(), N.current_stream(dev)), "fpc_kmeans_colsum")
     fpc_dist.chain_in_rank_order(_my_rows, carry, group)
-    mean0 = np.true_divide(carry.cpu().numpy(), int(n_total))          # float32 / int -> float32, as in np.mean
+    mean0 = np.true_divide(carry.cpu().numpy(), int(n_total))          # in the data's dtype, as in np.mean
     cb_full = torch.from_numpy(np.ascontiguousarray(codebook[:nb_entries])).to(dev)
     cb_full[0] = torch.from_numpy(mean0.astype(np.float64)).to(dev)
     n_draws = ndims * (nb_entries - 1) * nb_entries // 2

@@ -255,11 +255,18 @@ int fpc_kmeans_finalize(const double *d_sums, const double *d_counts, int K, dou
  * call divides, writes the statistics and leaves d_acc ZEROED for the next Lloyd iteration (cb_func.py:71-100 with no
  * memset / pack / unpack launches between the iterations).  n_total <= 0: the sum of the counts. */
 int fpc_kmeans_finalize_acc(double *d_acc, int K, double n_total, double *d_cb_out, double *d_stats, void *stream);
+/* The same for float64 vectors: the training data of a later stage, r = quantize(cb, r) - r, which the reference keeps
+ * in float64 (train_cb.py:200, cb_func.py:56-100).  The screen runs on the float32 rounding of a vector (inside its
+ * slack), near-ties are decided and the sums accumulated with the float64 vector.  CUDA-core kernel for every K. */
+int fpc_kmeans_assign_accumulate_f64(const double *d_data, long N, const double *d_cb, int K, double *d_sums,
+                                     double *d_counts, int32_t *d_idx, void *d_workspace, size_t workspace_bytes,
+                                     void *stream);
 /* d_carry[17] += column sums of the float32 rows IN ROW ORDER, in float32: the additions np.mean(data, 0) performs for
  * centroid 0 of vq_train (cb_func.py:34; NumPy reduces a C-contiguous (N,17) float32 array over axis 0 row by row in
  * float32).  Serial by nature: one CTA, ~8 ns per row.  Ranks of a sharded data set call it in rank order on the carry
  * of the previous rank. */
 int fpc_kmeans_colsum_f32(const float *d_data, long N, float *d_carry, void *stream);
+int fpc_kmeans_colsum_f64(const double *d_data, long N, double *d_carry, void *stream);   /* float64 rows, float64 additions */
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 
@@ -278,6 +285,10 @@ int fpc_compact_rows(const float *d_src, long n_rows, int src_stride, int col0, 
  * reference's, flipped relative to the encoder's x - csum) */
 int fpc_kmeans_stage_residual(const double *d_cb, int K, const int32_t *d_idx, const float *d_data, long N,
                               float *d_next, void *stream);
+/* next[i] = cb[idx[i]] - data[i] KEPT IN FLOAT64, as train_cb.py:200 leaves it (float64 codebook minus float32 data of
+ * the first stage, or minus the float64 data of a later one: data_is_f64) */
+int fpc_kmeans_stage_residual_f64(const double *d_cb, int K, const int32_t *d_idx, const void *d_data, int data_is_f64,
+                                  long N, double *d_next, void *stream);
 
 /* ---------------------------------------------------------------------------------------------
  * Receiver side and wire format of the index record idx (n_frames, 4) that fpc_encode writes.

@@ -470,6 +470,90 @@ int orc_kmeans_quantize(const float *data, long N, const double *cb, int K, int 
     return rc;
 }
 
+/* The same three functions for FLOAT64 training vectors: the data of a later training stage is
+ * r = quantize(cb, r) - r in float64 (train_cb.py:200), and numpy then evaluates (data - codebook) ** 2, the sums of
+ * `update` and the seed mean in float64 on it. */
+static double orc_dist_dd(const double *c, const double *x, int n)
+{
+    double e[ORC_MAX_DIM];
+    for (int d = 0; d < n; ++d) {
+        double t = x[d] - c[d];
+        e[d] = t * t;
+    }
+    if (n < 8) {
+        double res = 0.0;
+        for (int d = 0; d < n; ++d) res = res + e[d];
+        return res;
+    }
+    double r[8];
+    for (int j = 0; j < 8; ++j) r[j] = e[j];
+    int i;
+    for (i = 8; i < n - (n % 8); i += 8)
+        for (int j = 0; j < 8; ++j) r[j] = r[j] + e[i + j];
+    double res = ((r[0] + r[1]) + (r[2] + r[3])) + ((r[4] + r[5]) + (r[6] + r[7]));
+    for (; i < n; ++i) res = res + e[i];
+    return res;
+}
+
+int orc_find_nearest_d(const double *data, long N, const double *cb, int K, int ndim, int32_t *idx)
+{
+    if (ndim > ORC_MAX_DIM) return 1;
+#pragma omp parallel for schedule(static)
+    for (long i = 0; i < N; ++i) {
+        const double *x = data + (size_t)i * ndim;
+        double best = INFINITY;
+        int bi = 0;
+        for (int k = 0; k < K; ++k) {
+            double d = orc_dist_dd(cb + (size_t)k * ndim, x, ndim);
+            if (d < best || k == 0) { best = d; bi = k; }
+        }
+        idx[i] = bi;
+    }
+    return 0;
+}
+
+int orc_kmeans_update_d(const double *data, long N, const double *cb, int K, int ndim, double *cb_out,
+                        int32_t *idx_out /* may be NULL */, double *counts_out /* K, may be NULL */,
+                        double *stats /* 4, may be NULL */)
+{
+    int32_t *idx = idx_out ? idx_out : (int32_t *)malloc(sizeof(int32_t) * (size_t)N);
+    int rc = orc_find_nearest_d(data, N, cb, K, ndim, idx);
+    if (rc) { if (!idx_out) free(idx); return rc; }
+    double *count = (double *)calloc((size_t)K, sizeof(double));
+    memset(cb_out, 0, sizeof(double) * (size_t)K * ndim);
+    for (long i = 0; i < N; ++i) {
+        int n = idx[i];
+        count[n] += 1.0;
+        for (int d = 0; d < ndim; ++d) cb_out[(size_t)n * ndim + d] += data[(size_t)i * ndim + d];
+    }
+    double mn = INFINITY, mx = -INFINITY, empty = 0.0, w2 = 0.0;
+    for (int k = 0; k < K; ++k) {
+        for (int d = 0; d < ndim; ++d) cb_out[(size_t)k * ndim + d] /= (count[k] + 1e-20);
+        if (count[k] < mn) mn = count[k];
+        if (count[k] > mx) mx = count[k];
+        if (count[k] == 0.0) empty += 1.0;
+        double f = count[k] / (double)N;
+        w2 += f * f;
+    }
+    if (stats) { stats[0] = mn; stats[1] = mx; stats[2] = empty; stats[3] = w2; }
+    if (counts_out) memcpy(counts_out, count, sizeof(double) * (size_t)K);
+    free(count);
+    if (!idx_out) free(idx);
+    return 0;
+}
+
+int orc_kmeans_quantize_d(const double *data, long N, const double *cb, int K, int ndim, double *q_out,
+                          int32_t *idx_out)
+{
+    int32_t *idx = idx_out ? idx_out : (int32_t *)malloc(sizeof(int32_t) * (size_t)N);
+    int rc = orc_find_nearest_d(data, N, cb, K, ndim, idx);
+    if (!rc)
+        for (long i = 0; i < N; ++i)
+            memcpy(q_out + (size_t)i * ndim, cb + (size_t)idx[i] * ndim, sizeof(double) * (size_t)ndim);
+    if (!idx_out) free(idx);
+    return rc;
+}
+
 int orc_num_threads(void)
 {
 #ifdef _OPENMP

@@ -212,6 +212,43 @@ def run_kmeans_case():
     print("kmeans           done", flush=True)
 
 
+def run_kmeans_stages_case():
+    """The stage loop of train_cb.py:191-211 with the reference's own cb_func: the second stage trains on
+    r = quantize(cb, r) - r, which is FLOAT64 (float64 codebook minus float32 residual, :200)."""
+    import contextlib
+    import io
+    _, _, cb_func = ref_shim.load_reference()
+    r0 = S.make_kmeans_data(1500, seed=9, n_components=24)
+    n_entries = [8, 8]
+    out = {"data": r0, "n_entries": np.array(n_entries, np.int32), "train_seed": np.int32(4321)}
+    sink = io.StringIO()
+    with contextlib.redirect_stdout(sink):
+        # first batch (:193-200)
+        np.random.seed(4321)
+        r = r0
+        first = []
+        for i in range(2):
+            cb = cb_func.vq_train(r, np.zeros((n_entries[i], 17)), n_entries[i])
+            qr = cb_func.quantize(cb, r)
+            r = qr - r
+            first.append(cb)
+            out["first_r%d" % (i + 1)] = r
+        # a later batch (:205-211): ten updates per stage from the codebooks of the first
+        r = r0
+        later = []
+        for i in range(2):
+            cb = first[i]
+            for _ in range(10):
+                cb = cb_func.update(r, cb, n_entries[i])
+            qr = cb_func.quantize(cb, r)
+            r = qr - r
+            later.append(cb)
+    assert out["first_r1"].dtype == np.float64
+    out.update(first_cb0=first[0], first_cb1=first[1], later_cb0=later[0], later_cb1=later[1])
+    np.savez_compressed(os.path.join(GOLDEN, "kmeans_stages.npz"), **out)
+    print("kmeans_stages    done", flush=True)
+
+
 def run_ceps2lpc_case():
     """ceps2lpc_v (ceps2lpc/ceps2lpc_vct.py:122-162) on de-normalised synthetic cepstra (x 24.1, as the callers do at
     synthesis_qtz.py:158) incl. an all-zero frame and a ramp."""
@@ -235,6 +272,7 @@ CASES = {
     "ceps2lpc": run_ceps2lpc_case,
     "quantizers": run_quantizer_case,
     "kmeans": run_kmeans_case,
+    "kmeans_stages": run_kmeans_stages_case,
     # BASELINE.json configs[0]: 3 utterances x 3 s, README thresholds
     "cfg1_readme": lambda: run_encoder_case("cfg1_readme", 3, 300, S.L1_README, S.L2_README),
     # calibrated thresholds (about half the frames below) so both branches are exercised

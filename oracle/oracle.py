@@ -51,6 +51,15 @@ def _f32(a):
     return np.ascontiguousarray(a, dtype=np.float32)
 
 
+def _train_data(a):
+    """Training vectors keep float64 when they are float64 (a later stage's `quantize(cb, r) - r`, train_cb.py:200);
+    everything else is float32, what the encoder's residuals are.  Returns (array, suffix of the C entry points)."""
+    a = np.asarray(a)
+    if a.dtype == np.float64:
+        return np.ascontiguousarray(a), "_d"
+    return _f32(a), ""
+
+
 def weights_from_state_dict(sd):
     """state_dict (torch tensors or ndarrays, keys as wavernn.py:37-38,48-52) -> dict of f32 arrays."""
     out = {}
@@ -229,10 +238,10 @@ def scl_quantize(codes, x):
 
 def find_nearest(data, codebook):
     """cb_func.find_nearest (cb_func.py:56-68)."""
-    data = _f32(data)
+    data, suf = _train_data(data)
     cb = np.ascontiguousarray(codebook, dtype=np.float64)
     idx = np.zeros(len(data), np.int32)
-    rc = lib().orc_find_nearest(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(len(cb)),
+    rc = getattr(lib(), "orc_find_nearest" + suf)(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(len(cb)),
                                 ctypes.c_int(data.shape[1]), _p(idx))
     if rc:
         raise RuntimeError("orc_find_nearest failed with status %d" % rc)
@@ -241,15 +250,15 @@ def find_nearest(data, codebook):
 
 def kmeans_update(data, codebook, with_details=False):
     """cb_func.update (cb_func.py:71-100): one Lloyd iteration -> new (K,ndim) float64 codebook."""
-    data = _f32(data)
+    data, suf = _train_data(data)
     cb = np.ascontiguousarray(codebook, dtype=np.float64)
     K, nd = cb.shape
     out = np.zeros((K, nd), np.float64)
     idx = np.zeros(len(data), np.int32)
     counts = np.zeros(K, np.float64)
     stats = np.zeros(4, np.float64)
-    rc = lib().orc_kmeans_update(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(K), ctypes.c_int(nd),
-                                 _p(out), _p(idx), _p(counts), _p(stats))
+    rc = getattr(lib(), "orc_kmeans_update" + suf)(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(K), ctypes.c_int(nd),
+                                                   _p(out), _p(idx), _p(counts), _p(stats))
     if rc:
         raise RuntimeError("orc_kmeans_update failed with status %d" % rc)
     if with_details:
@@ -259,12 +268,12 @@ def kmeans_update(data, codebook, with_details=False):
 
 def kmeans_quantize(codebook, data):
     """cb_func.quantize (cb_func.py:103-112)."""
-    data = _f32(data)
+    data, suf = _train_data(data)
     cb = np.ascontiguousarray(codebook, dtype=np.float64)
     q = np.zeros((len(data), cb.shape[1]), np.float64)
     idx = np.zeros(len(data), np.int32)
-    rc = lib().orc_kmeans_quantize(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(len(cb)),
-                                   ctypes.c_int(cb.shape[1]), _p(q), _p(idx))
+    rc = getattr(lib(), "orc_kmeans_quantize" + suf)(_p(data), ctypes.c_long(len(data)), _p(cb), ctypes.c_int(len(cb)),
+                                                     ctypes.c_int(cb.shape[1]), _p(q), _p(idx))
     if rc:
         raise RuntimeError("orc_kmeans_quantize failed with status %d" % rc)
     return q, idx
@@ -274,7 +283,7 @@ def vq_train(data, codebook, nb_entries, rng):
     """cb_func.vq_train (cb_func.py:28-54): grow-by-one LBG.  `rng` supplies the jitter the
     reference draws from numpy's global RNG (np.random.rand(e, ndims)), so a seeded
     np.random.RandomState reproduces a seeded reference run."""
-    data = _f32(data)
+    data, _ = _train_data(data)
     codebook = np.array(codebook, dtype=np.float64, copy=True)
     ndims = data.shape[1]
     codebook[0] = np.mean(data, 0)

@@ -84,16 +84,21 @@ def test_stage_residual_and_train_stages(torch_cuda, synth, oracle):
     rng = np.random.RandomState(11)
     cb = rng.randn(64, 17) * 0.1
     nxt = fpc_train.stage_residual(cb, d).cpu().numpy()
-    # train_cb.py:199-200 in NumPy: qr = quantize(codebook, r); r = qr - r
+    # train_cb.py:199-200 in NumPy: qr = quantize(codebook, r); r = qr - r   (float64, as the reference leaves it)
     idx = oracle.find_nearest(data, cb)
-    want = (cb[idx] - data).astype(np.float32)
-    assert np.array_equal(nxt, want)
+    want = cb[idx] - data
+    assert nxt.dtype == np.float64 and np.array_equal(nxt, want)
+    assert np.array_equal(fpc_train.stage_residual(cb, d, keep_float64=False).cpu().numpy(), want.astype(np.float32))
+    # ... and once more from the float64 vectors of a second stage
+    cb2 = rng.randn(32, 17) * 0.03
+    nxt2 = fpc_train.stage_residual(cb2, torch.from_numpy(want).cuda()).cpu().numpy()
+    assert np.array_equal(nxt2, cb2[oracle.find_nearest(want, cb2)] - want)
     # two stages of 8 entries: stage 2 trains on the flipped residual of stage 1 and reduces the error
     cbs = fpc_train.train_stages(d, [8, 8], rng=np.random.RandomState(0))
     assert len(cbs) == 2 and cbs[0].shape == (8, 17) and cbs[1].shape == (8, 17)
     q1 = cb_func.quantize(cbs[0], data)
     r1 = q1 - data
-    q2 = cb_func.quantize(cbs[1], r1.astype(np.float32))
+    q2 = cb_func.quantize(cbs[1], r1)
     e1 = float((r1 ** 2).sum())
     e2 = float(((q2 - r1) ** 2).sum())
     assert e2 < e1
@@ -101,8 +106,8 @@ def test_stage_residual_and_train_stages(torch_cuda, synth, oracle):
 
 def test_train_stages_later_batches_vs_oracle(torch_cuda, synth, oracle):
     """train_cb.py:205-211 -- every batch after the first: for each stage ten `update` calls on the incoming
-    codebook, then r = quantize(cb, r) - r feeds the next stage.  Restated here with the oracle's update / find_nearest
-    (next-stage data rounded to float32 as the product does, fpc_train.py) and compared codebook by codebook."""
+    codebook, then r = quantize(cb, r) - r (float64) feeds the next stage.  Restated here with the oracle's update /
+    find_nearest and compared codebook by codebook."""
     import fpc_train
     torch = torch_cuda
     data = synth.make_kmeans_data(30000, seed=9, n_components=96)
@@ -117,10 +122,55 @@ def test_train_stages_later_batches_vs_oracle(torch_cuda, synth, oracle):
             cb = oracle.kmeans_update(r, cb)
         np.testing.assert_allclose(got[i], cb, rtol=1e-9, atol=1e-300, err_msg="stage %d" % i)
         idx = oracle.find_nearest(r, cb)
-        r = (cb[idx] - r).astype(np.float32)
+        r = cb[idx] - r
     # the incoming codebooks were used: a different start gives a different result
     other = fpc_train.train_stages(d, [32, 16], codebooks=[c[::-1].copy() * 1.5 for c in cb_in], first_batch=False)
     assert not np.allclose(other[0], got[0])
+
+
+def test_two_stage_training_matches_the_reference(torch_cuda):
+    """tests/golden/kmeans_stages.npz: the stage loop of train_cb.py:191-211 run with the reference's own cb_func
+    (oracle/gen_golden.py).  The second stage trains on float64 vectors, as in the reference; what is left between the
+    two runs is the order of the float64 additions inside `update` (1e-12 per iteration, chained over the schedule)."""
+    import fpc_train
+    from helpers import load_golden
+    torch = torch_cuda
+    g = load_golden("kmeans_stages")
+    data = torch.from_numpy(g["data"]).cuda()
+    n_entries = [int(k) for k in g["n_entries"]]
+    first = fpc_train.train_stages(data, n_entries, rng=np.random.RandomState(int(g["train_seed"])))
+    for i in range(2):
+        np.testing.assert_allclose(first[i], g["first_cb%d" % i], rtol=1e-10, atol=1e-300, err_msg="first batch, stage %d" % i)
+    # the float64 residual of the first stage, bit for bit, from the reference's codebook
+    r1 = fpc_train.stage_residual(g["first_cb0"], data)
+    assert r1.dtype == torch.float64 and np.array_equal(r1.cpu().numpy(), g["first_r1"])
+    later = fpc_train.train_stages(data, n_entries, codebooks=[g["first_cb0"], g["first_cb1"]], first_batch=False)
+    for i in range(2):
+        np.testing.assert_allclose(later[i], g["later_cb%d" % i], rtol=1e-10, atol=1e-300, err_msg="later batch, stage %d" % i)
+
+
+def test_kmeans_float64_vectors_vs_oracle(torch_cuda, synth, oracle):
+    """The float64-vector entry points: indices bit-exact (incl. vectors whose float32 rounding would pick another
+    centroid), sums / centroids to 1e-12, for small and large K, and the row-order float64 mean."""
+    import fpc_native as N
+    from quantization import cb_func
+    torch = torch_cuda
+    g = np.random.Generator(np.random.Philox(key=41))
+    for n, K in ((5000, 7), (40000, 200), (30000, 1024)):
+        data = synth.make_kmeans_data(n, seed=42, n_components=64).astype(np.float64)
+        data += g.standard_normal(data.shape) * 1e-9                 # not float32-representable
+        cb = g.standard_normal((K, 17)) * 0.1
+        if K >= 7:
+            cb[5] = cb[2]
+            mid = 0.5 * (cb[0] + cb[1])
+            data[:64] = mid + g.standard_normal((64, 17)) * 1e-12    # closer than float32 resolution to a bisector
+        assert np.array_equal(cb_func.find_nearest(data, cb), oracle.find_nearest(data, cb).astype(np.int64))
+        new = cb_func.update(data, cb, K, verbose=False)
+        np.testing.assert_allclose(new, oracle.kmeans_update(data, cb), rtol=1e-12, atol=1e-300)
+        d = torch.from_numpy(data).cuda()
+        carry = torch.zeros(17, dtype=torch.float64, device="cuda")
+        N.check(N.lib().fpc_kmeans_colsum_f64(d.data_ptr(), n, carry.data_ptr(), N.current_stream(d.device)), "colsum")
+        assert np.array_equal(np.true_divide(carry.cpu().numpy(), n), np.mean(data, 0))
 
 
 def test_scalar_codebook_is_a_lloyd_fixed_point(torch_cuda):

@@ -64,6 +64,29 @@ def test_kmeans_matches_reference(oracle):
     assert np.array_equal(cbt, g["train_cb"])
 
 
+def test_two_stage_training_matches_reference(oracle):
+    """The stage loop of train_cb.py:191-211 (first batch and a later batch): the second stage runs on the float64
+    residual quantize(cb, r) - r, and the oracle reproduces the reference's codebooks bit for bit."""
+    g = load_golden("kmeans_stages")
+    n_entries = [int(k) for k in g["n_entries"]]
+    rng = np.random.RandomState(int(g["train_seed"]))
+    r = g["data"]
+    for i, K in enumerate(n_entries):
+        cb = oracle.vq_train(r, np.zeros((K, 17)), K, rng)
+        assert np.array_equal(cb, g["first_cb%d" % i])
+        q, _ = oracle.kmeans_quantize(cb, r)
+        r = q - r
+        assert r.dtype == np.float64 and np.array_equal(r, g["first_r%d" % (i + 1)])
+    r = g["data"]
+    for i, K in enumerate(n_entries):
+        cb = g["first_cb%d" % i]
+        for _ in range(10):
+            cb = oracle.kmeans_update(r, cb)
+        assert np.array_equal(cb, g["later_cb%d" % i])
+        q, _ = oracle.kmeans_quantize(cb, r)
+        r = q - r
+
+
 @pytest.mark.parametrize("case", ENCODER_CASES)
 def test_encoder_matches_reference(oracle, oracle_weights, state_dict, synth, case):
     g = load_golden(case)

@@ -122,7 +122,7 @@ template <int NU> struct SmemB {
     // misc: m1[NU] m2[NU] (float), idx0/idx1/idx2[NU], listA[NU], listB[NU] (int), counts[4], tmem base, pad
     static constexpr int offScl = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;      // both scalar tables, file dtype, 2 x 2 KB + {n, dtype} x 2
     static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8 + 16;
-    static constexpr int kNumBars = 2 * kBStages + 3;
+    static constexpr int kNumBars = 2 * kBStages + 4;
     static constexpr int kBase = ((offBars + kNumBars * 8 + 127) / 128) * 128;
     static constexpr int kScratchBytes = kX1Bytes;   // the dead [x | h1] tile doubles as VQ scratch
     // Tensor-core VQ screen (fpc_vq_tc.cuh).  The A tiles live in the scratch when they fit (64-utterance tiles: 3 x 16 KB
@@ -142,6 +142,12 @@ template <int NU> struct SmemB {
     // 1.4 k cycles per chunk, tools/phase_profile.py trace).
     static constexpr int kNB = 2;
     static constexpr int total = offBring + kNB * kVtChunkBytes;
+    // During the VQ phase of a frame the weight ring of the gate GEMMs is idle -- if its producer is held back until
+    // the phase is over (it then refills the ring under the feedback phase, before GRU 1 of the next frame needs it).
+    // The screen uses that memory as further ring slots: with two slots only, every codebook copy (~650 cycles from L2)
+    // was serialised with the MMAs of the chunk before it (tools/phase_profile.py trace, round 2).
+    static constexpr int kNBLent = (kBStages * kBStageBytes) / kVtChunkBytes;      // 4
+    static constexpr int kNBTotal = kNB + kNBLent;
     static_assert(total <= 227 * 1024, "shared memory");
 };
 
@@ -225,19 +231,22 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     uint64_t *acc_full = empty + kBStages;
     uint64_t *acc_empty = acc_full + 1;
     uint64_t *act_ready = acc_empty + 1;
+    uint64_t *vq_done = act_ready + 1;        // compute warps -> weight producer: the screen no longer uses the weight ring
 
     const int tid = threadIdx.x;
     const int warp = tid >> 5, lane = tid & 31;
     const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
-    VqTcShared<S::kNB> *vsh = reinterpret_cast<VqTcShared<S::kNB> *>(smem + S::offVqSh);
-    static_assert(sizeof(VqTcShared<S::kNB>) <= 512, "control block");
+    VqTcShared<S::kNBTotal> *vsh = reinterpret_cast<VqTcShared<S::kNBTotal> *>(smem + S::offVqSh);
+    static_assert(sizeof(VqTcShared<S::kNBTotal>) <= 512, "control block");
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }      // three issuing warps
         mbar_init(acc_full, 3);
         mbar_init(acc_empty, kComputeThreads / 32);
         mbar_init(act_ready, kComputeThreads / 32);
-        vq_tc_init<S::kNB>(vsh, kComputeThreads / 32);
+        mbar_init(vq_done, 1);
+        vq_tc_init<S::kNBTotal>(vsh, kComputeThreads / 32);
+        vsh->ring2_addr = smem_u32(smem + S::offRing);
         mbar_fence_init();
     }
     // all 512 columns: the gate accumulators use 4 NU of them; the VQ screen uses all of them while the gate
@@ -260,12 +269,14 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             const long long total = (long long)my_tiles * (P.f1 - P.f0) * kBStepsPerFrame;
             const char *src = reinterpret_cast<const char *>(P.wstream);
             int s = 0, gf = 0;
-            uint32_t wraps = 0;
+            uint32_t wraps = 0, frames = 0;
+            const bool lend = P.mode == kModeQuantize;         // the ring is lent to the VQ screen between two frames
             for (long long g = 0; g < total; ++g) {
+                if (lend && gf == 0 && frames > 0) mbar_wait(vq_done, (frames - 1) & 1u);
                 if (wraps > 0) mbar_wait(&empty[s], (wraps - 1) & 1u);
                 mbar_arrive_expect_tx(&full[s], kBStageBytes);
                 bulk_g2s(smem + S::offRing + s * kBStageBytes, src + (size_t)gf * kBStageBytes, kBStageBytes, &full[s]);
-                if (++gf == kBStepsPerFrame) gf = 0;
+                if (++gf == kBStepsPerFrame) { gf = 0; ++frames; }
                 if (++s == kBStages) { s = 0; ++wraps; }
             }
         } else if (warp > kComputeThreads / 32) {
@@ -328,10 +339,10 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                         bool done = false;
                         if (gate == 1) {
                             if (lane == 0)
-                                while (!done) done = vq_tc_produce_phase<S::kNB>(vsh, P.cb, vn);
+                                while (!done) done = vq_tc_produce_phase<S::kNBTotal>(vsh, P.cb, vn);
                             __syncwarp();
                         } else {
-                            while (!done) done = vq_tc_issue_phase<S::kNB>(vsh, tb, vn, lane, gate >> 1);
+                            while (!done) done = vq_tc_issue_phase<S::kNBTotal>(vsh, tb, vn, lane, gate >> 1);
                         }
                     }
                 }
@@ -547,10 +558,13 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     for (int book = 0; book < 2; ++book) {
                         const int nrows = book ? nB : nA;
                         if (nrows > 0)
-                            vq_tc_dispatch<NU, S::kNB>(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, rs, rq, idx1s, idx2s,
+                            vq_tc_dispatch<NU, S::kNBTotal>(book ? cbh->bl : cbh->vq, P.cb, book ? listB : listA, nrows, rs, rq, idx1s, idx2s,
                                                        vmem, vsh, (book == 1 || !tcB) ? 1 : 0, tid, prof ? pt + kPhVqDbg : nullptr);
                     }
-                    if (!(nA > 0 && cbh->vq.K >= 64) && !tcB) vq_tc_publish_idle<S::kNB>(vsh, tid);
+                    if (!(nA > 0 && cbh->vq.K >= 64) && !tcB) vq_tc_publish_idle<S::kNBTotal>(vsh, tid);
+                    // every accumulator unit of the frame has been read, so every MMA that read a codebook chunk is complete:
+                    // the weight producer may refill its ring
+                    if (tid == 0) mbar_arrive(vq_done);
                 }
             } else {
                 named_bar_sync(1, kComputeThreads);

@@ -56,17 +56,26 @@ template <int NB, int UNITS = kVtUnits> struct VqTcShared {
     // whole frame loop, and the gate GEMM of the fp32 kernel has no register to spare (six more spilled inside its
     // inner loop and cost 12 % of the frame).
     uint32_t tmem_base, cnt_go, cnt_b, cnt_u;
+    // ring slots beyond the first kVtOwnSlots live elsewhere in shared memory (the bf16 kernel lends the idle weight ring
+    // of the gate GEMMs to the screen); 0 = none.  Set once by the kernel.
+    uint32_t ring2_addr;
     long long *trace;             // debug (tools/phase_profile.py): event times of the first phases of CTA 0, or null
     uint64_t go, ack;
     uint64_t b_full[NB], b_empty[NB];
     uint64_t d_full[UNITS], d_empty[UNITS];
 };
+constexpr int kVtOwnSlots = 2;
+__device__ __forceinline__ uint32_t vq_tc_slot_addr(uint32_t ring, uint32_t ring2, int slot)
+{
+    return slot < kVtOwnSlots ? ring + (uint32_t)slot * kVtChunkBytes : ring2 + (uint32_t)(slot - kVtOwnSlots) * kVtChunkBytes;
+}
 struct VqTcCount { uint32_t go, b, u, ring; };       // running use counts of one role (phases, B chunks, TMEM units); ring address in use
 
 template <int NB, int UNITS>
 __device__ __forceinline__ void vq_tc_init(VqTcShared<NB, UNITS> *sh, int compute_warps)
 {
     sh->cnt_go = sh->cnt_b = sh->cnt_u = 0u;
+    sh->ring2_addr = 0u;
     sh->trace = nullptr;
     mbar_init(&sh->go, 1);
     mbar_init(&sh->ack, 3);            // two issuing warps + the streamer
@@ -101,7 +110,7 @@ __device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB, UNITS> *sh, c
     mbar_wait_idle(&sh->go, n.go & 1u); ++n.go;
     const int nchunks = sh->ctl.p_nchunks, last = sh->ctl.last;
     const long long off = sh->ctl.b_off;
-    const uint32_t ring = sh->ctl.ring_addr;
+    const uint32_t ring = sh->ctl.ring_addr, ring2 = sh->ring2_addr;
     mbar_arrive(&sh->ack);
     for (int c = 0; c < nchunks; ++c, ++n.b) {
         const int bs = (int)(n.b % NB);
@@ -109,7 +118,7 @@ __device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB, UNITS> *sh, c
         if (use > 0) mbar_wait(&sh->b_empty[bs], (use - 1) & 1u);
         if (sh->trace && n.b < 64) sh->trace[n.b] = clock64();
         mbar_arrive_expect_tx(&sh->b_full[bs], kVtChunkBytes);
-        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(ring + bs * kVtChunkBytes),
+        asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(vq_tc_slot_addr(ring, ring2, bs)),
                      "l"(cbbase + off + (long long)c * kVtChunkBytes), "r"((uint32_t)kVtChunkBytes), "r"(smem_u32(&sh->b_full[bs]))
                      : "memory");
     }
@@ -133,7 +142,8 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
     umma::fence_after_sync();
     const uint32_t idesc = tc::instr_desc_f16(128, 64);
     // descriptors differ only in their address field (bytes >> 4, low 14 bits): one base each, then additions
-    const uint64_t adesc0 = umma::smem_desc(a_addr, 128), bdesc0 = umma::smem_desc(bring_addr, 64);
+    const uint64_t adesc0 = umma::smem_desc(a_addr, 128);
+    const uint32_t ring2 = sh->ring2_addr;
     for (int c = 0; c < nchunks; ++c, ++n.b) {
         if ((c & 1) != which) { n.u += mtiles; continue; }       // the other issuing warp's chunk
         const int bs = (int)(n.b % NB);
@@ -147,7 +157,7 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
             }
         umma::fence_after_sync();
         if (lane == 0 && sh->trace && n.b < 64) sh->trace[192 + n.b] = clock64();
-        const uint64_t bd = bdesc0 + (uint64_t)((bs * kVtChunkBytes) >> 4);
+        const uint64_t bd = umma::smem_desc(vq_tc_slot_addr(bring_addr, ring2, bs), 64);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
 #pragma unroll

@@ -234,7 +234,10 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     uint64_t *vq_done = act_ready + 1;        // compute warps -> weight producer: the screen no longer uses the weight ring
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    // The warp index through a shuffle: the compiler then KNOWS it is the same in all lanes.  With tid >> 5 every branch on
+    // the warp's role counted as divergent, and inside such a region every tcgen05.mma was issued through ELECT + five
+    // R2UR.BROADCAST (~200 cycles per MMA instead of ~10: the descriptors did not stay on the uniform datapath).
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
 
     VqTcShared<S::kNBTotal> *vsh = reinterpret_cast<VqTcShared<S::kNBTotal> *>(smem + S::offVqSh);
@@ -265,7 +268,10 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     if (warp >= kComputeThreads / 32) {
         // 256 x 216 + 128 x 72 = 64 512 = 384 x 168 (the launch allocation): the increase can always be granted
         asm volatile("setmaxnreg.dec.sync.aligned.u32 72;");
-        if (warp == kComputeThreads / 32 && lane == 0) {
+        // (warp first, lane inside: a condition that mixes the lane in would make the issuing warps' whole branch count as
+        // divergent for the compiler, with the slow tcgen05.mma issue sequence that goes with it)
+        if (warp == kComputeThreads / 32) {
+          if (lane == 0) {
             const long long total = (long long)my_tiles * (P.f1 - P.f0) * kBStepsPerFrame;
             const char *src = reinterpret_cast<const char *>(P.wstream);
             int s = 0, gf = 0;
@@ -279,7 +285,18 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                 if (++gf == kBStepsPerFrame) { gf = 0; ++frames; }
                 if (++s == kBStages) { s = 0; ++wraps; }
             }
-        } else if (warp > kComputeThreads / 32) {
+          } else if (lane == 1 && P.mode == kModeQuantize) {
+            // the codebook images of the VQ screen, streamed by another lane of this warp.  (Not by one of the issuing
+            // warps: a region under `lane == ...` inside their frame loop makes the compiler treat the rest of the loop as
+            // not converged, and every tcgen05.mma is then issued through ELECT + five R2UR.BROADCAST, ~200 cycles each.)
+            VqTcCount vn_stream{0u, 0u, 0u, 0u};
+            const long long frames = (long long)my_tiles * (P.f1 - P.f0);
+            for (long long f = 0; f < frames; ++f) {
+                bool done = false;
+                while (!done) done = vq_tc_produce_phase<S::kNBTotal>(vsh, P.cb, vn_stream);
+            }
+          }
+        } else {
             // MMA issuers: warps 9, 10, 11, one GATE each (r, z, n -- separate accumulators, so the split does not touch
             // any summation order).  A single thread needs ~100-200 cycles per tcgen05 instruction (descriptor moves to
             // the uniform datapath, issue), which made the 330 MMAs of a frame as long as the whole GRU phase; three
@@ -288,7 +305,8 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             const int gate = warp - (kComputeThreads / 32 + 1);          // 0 = r, 1 = z, 2 = n
             const uint32_t idesc = umma::instr_desc_bf16(128, NU);
             const uint32_t ring_a = smem_u32(smem + S::offRing);
-            const uint32_t x1a[2] = {smem_u32(x1[0]), smem_u32(x1[1])};
+            const uint32_t x1a0 = smem_u32(x1[0]);       // (the two [x | h1] tiles are adjacent: address arithmetic instead of an indexed
+                                                          //  local array keeps the descriptors on the uniform datapath)
             const uint32_t h2a = smem_u32(h2t);
             int s = 0;
             uint32_t ph = 0, n_act = 0, n_acc = 0;
@@ -305,10 +323,10 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                             mbar_wait(&full[s], ph);
                             umma::fence_after_sync();
                             const uint32_t a0 = ring_a + s * kBStageBytes + gate * kBTileBytes;
-                            const uint64_t bd = umma::smem_desc(x1a[cur] + (uint32_t)(2 * i) * (NU * 16), NU);
-                            if (gate < 2) umma::mma_bf16_elect(tb + gate * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                            else if (i < 2) umma::mma_bf16_elect(tb + 2 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                            else umma::mma_bf16_elect(tb + 3 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 2);
+                            const uint64_t bd = umma::smem_desc(x1a0 + (uint32_t)cur * S::kX1Bytes + (uint32_t)(2 * i) * (NU * 16), NU);
+                            // gates r, z: one accumulator over x and h; gate n: n_i over the two x steps, n_h over the h steps
+                            const bool nh = gate == 2 && i >= 2;
+                            umma::mma_bf16_elect(tb + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > 2 : i > 0);
                             umma::commit_elect(&empty[s]);
                             if (++s == kBStages) { s = 0; ph ^= 1u; }
                         }
@@ -323,27 +341,20 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                         umma::fence_after_sync();
                         const uint32_t a0 = ring_a + s * kBStageBytes + gate * kBTileBytes;
                         const bool xp = i < kH1 / 16;
-                        const uint32_t baddr = xp ? x1a[cur ^ 1] + (uint32_t)(4 + 2 * i) * (NU * 16)
+                        const uint32_t baddr = xp ? x1a0 + (uint32_t)(cur ^ 1) * S::kX1Bytes + (uint32_t)(4 + 2 * i) * (NU * 16)
                                                   : h2a + (uint32_t)(2 * (i - kH1 / 16)) * (NU * 16);
                         const uint64_t bd = umma::smem_desc(baddr, NU);
-                        if (gate < 2) umma::mma_bf16_elect(tb + gate * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                        else if (xp) umma::mma_bf16_elect(tb + 2 * NU, umma::smem_desc(a0, 128), bd, idesc, i > 0);
-                        else umma::mma_bf16_elect(tb + 3 * NU, umma::smem_desc(a0, 128), bd, idesc, i > kH1 / 16);
+                        const bool nh = gate == 2 && !xp;
+                        umma::mma_bf16_elect(tb + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > kH1 / 16 : i > 0);
                         umma::commit_elect(&empty[s]);
                         if (++s == kBStages) { s = 0; ph ^= 1u; }
                     }
                     umma::commit_elect(acc_full);
                     cur ^= 1;
                     // the searches of this frame: stages of the codebooks as published by the compute warps
-                    if (P.mode == kModeQuantize) {
+                    if (P.mode == kModeQuantize && gate != 1) {      // warps 9 and 11 issue alternate chunks
                         bool done = false;
-                        if (gate == 1) {
-                            if (lane == 0)
-                                while (!done) done = vq_tc_produce_phase<S::kNBTotal>(vsh, P.cb, vn);
-                            __syncwarp();
-                        } else {
-                            while (!done) done = vq_tc_issue_phase<S::kNBTotal>(vsh, tb, vn, lane, gate >> 1);
-                        }
+                        while (!done) done = vq_tc_issue_phase<S::kNBTotal>(vsh, tb, vn, lane, gate >> 1);
                     }
                 }
             }

@@ -392,7 +392,10 @@ __global__ void __launch_bounds__(kThreads, 1) encode_fp32_kernel(EncodeParams P
     static_assert(sizeof(VqSh) <= 512, "control block");
 
     const int tid = threadIdx.x;
-    const int warp = tid >> 5, lane = tid & 31;
+    // The warp index through a shuffle: the compiler then KNOWS it is the same in all lanes.  With tid >> 5 every branch on
+    // the warp's role counted as divergent, and inside such a region every tcgen05.mma was issued through ELECT + five
+    // R2UR.BROADCAST (~200 cycles per MMA instead of ~10: the descriptors did not stay on the uniform datapath).
+    const int warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;
     const int my_tiles = P.ntiles > (int)blockIdx.x ? (P.ntiles - 1 - (int)blockIdx.x) / (int)gridDim.x + 1 : 0;
     const int nframes = P.f1 - P.f0;
 

@@ -125,6 +125,15 @@ __device__ __forceinline__ bool vq_tc_produce_phase(VqTcShared<NB, UNITS> *sh, c
     return last != 0;
 }
 
+// Event times of the first chunks for tools/phase_profile.py -- in debug builds only (-DFPC_VQ_TRACE_ON): a branch on the
+// lane inside the issue loop makes the compiler treat the whole loop as divergent, and every tcgen05.mma is then issued
+// through ELECT + five R2UR.BROADCAST (~200 cycles per MMA) instead of straight from uniform registers.
+#ifdef FPC_VQ_TRACE_ON
+#define FPC_VQ_TRACE(slot) do { if (lane == 0 && sh->trace && n.b < 64) sh->trace[(slot) + n.b] = clock64(); } while (0)
+#else
+#define FPC_VQ_TRACE(slot) do { } while (0)
+#endif
+
 // ---- MMA issuer WARPS (two of them, `which` = 0 / 1, alternate chunks; all 32 lanes run the loop converged and one
 //      elected lane issues): one phase ----
 template <int NB, int UNITS>
@@ -148,7 +157,7 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
         if ((c & 1) != which) { n.u += mtiles; continue; }       // the other issuing warp's chunk
         const int bs = (int)(n.b % NB);
         mbar_wait(&sh->b_full[bs], (n.b / NB) & 1u);
-        if (lane == 0 && sh->trace && n.b < 64) sh->trace[64 + n.b] = clock64();
+        FPC_VQ_TRACE(64);
 #pragma unroll
         for (int m = 0; m < 3; ++m)
             if (m < mtiles) {
@@ -156,7 +165,7 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
                 if (use > 0) mbar_wait(&sh->d_empty[(n.u + m) % UNITS], (use - 1) & 1u);
             }
         umma::fence_after_sync();
-        if (lane == 0 && sh->trace && n.b < 64) sh->trace[192 + n.b] = clock64();
+        FPC_VQ_TRACE(192);
         const uint64_t bd = umma::smem_desc(vq_tc_slot_addr(bring_addr, ring2, bs), 64);
 #pragma unroll
         for (int ks = 0; ks < 4; ++ks) {
@@ -166,12 +175,12 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
                     umma::mma_bf16_elect(tb + ((n.u + m) % UNITS) * 64u, adesc0 + (uint64_t)((m * tc::kTileBytes + ks * tc::kSlabBytes) >> 4),
                                          bd + (uint64_t)((ks * kVtSlabBytes) >> 4), idesc, ks > 0);
         }
-        if (lane == 0 && sh->trace && n.b < 64) sh->trace[320 + n.b] = clock64();
+        FPC_VQ_TRACE(320);
 #pragma unroll
         for (int m = 0; m < 3; ++m)
             if (m < mtiles) umma::commit_elect(&sh->d_full[(n.u + m) % UNITS]);
         umma::commit_elect(&sh->b_empty[bs]);
-        if (lane == 0 && sh->trace && n.b < 64) sh->trace[128 + n.b] = clock64();
+        FPC_VQ_TRACE(128);
         n.u += mtiles;
     }
     return last != 0;

@@ -29,7 +29,9 @@ namespace fpc {
 constexpr int kTcScanWarps = 8;
 constexpr int kTcColParts = kTcScanWarps / 4;                  // column parts of a 128-centroid chunk (one per warp of a lane quarter)
 constexpr int kTcLdPerUnit = 128 / (32 * kTcColParts);         // 32-column TMEM loads per thread and chunk
-constexpr int kTcScan = 32 * kTcScanWarps, kTcLoad = 96, kTcThreads = kTcScan + kTcLoad + 32;   // a multiple of 128 threads
+// roles: kTcScanWarps scanning warps, two converting ("loader") warps, one warp whose lane 0 issues the bulk copies, one
+// warp that issues the MMAs
+constexpr int kTcScan = 32 * kTcScanWarps, kTcLoad = 64, kTcThreads = kTcScan + kTcLoad + 64;   // a multiple of 128 threads
 constexpr int kTcASlots = 2, kTcDSlots = 4, kTcRawSlots = 4;
 constexpr int kTcRawFloats = 128 * kDim;           // one tile of the data set: 8704 contiguous bytes
 constexpr int kTcShadowLd = 20;                    // fp32 shadow row: c0..c16, -, ||c||^2, -
@@ -190,7 +192,7 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
              *d_empty = d_full + kTcDSlots, *raw_full = d_empty + kTcDSlots, *raw_empty = raw_full + kTcRawSlots;
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kTcRawSlots);
 
-    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // (warp index known to be uniform)
     const long my_tiles = ntiles > (long)blockIdx.x ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
 
     if (tid == 0) {
@@ -214,35 +216,38 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
     auto tile_is_bulk = [&](long t) { return (t + 1) * 128 <= N; };
 
     if (warp == kTcThreads / 32 - 1) {
+        // ---------------- MMA issuer: the whole warp runs the loop converged, one elected lane issues ----------------
+        // (Issued from an `if (lane == 0)` region every tcgen05.mma goes through ELECT + R2UR sequences, 100-200 cycles
+        //  each -- more than the tensor pipe needs for the MMA; in a warp-uniform loop the descriptors stay in uniform
+        //  registers.  Nothing lane-dependent may sit in this warp's loop: the copies are issued by the warp before it.)
+        mbar_wait(b_full, 0);            // the codebook image
+        const uint32_t idesc = tc::instr_desc_f16(128, 128);
+        const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
+        uint32_t u = 0;
+        for (long i = 0; i < my_tiles; ++i) {
+            const int sa = (int)(i % kTcASlots);
+            const uint32_t na = (uint32_t)(i / kTcASlots);
+            mbar_wait(&a_full[sa], na & 1u);
+            umma::fence_after_sync();
+            for (int c = 0; c < nchunks; ++c, ++u) {
+                const int ds = (int)(u % kTcDSlots);
+                const uint32_t nd = u / kTcDSlots;
+                if (nd > 0) { mbar_wait(&d_empty[ds], (nd - 1) & 1u); umma::fence_after_sync(); }
+#pragma unroll
+                for (int ks = 0; ks < 4; ++ks)
+                    umma::mma_bf16_elect(tb + (uint32_t)ds * 128u, umma::smem_desc(a0 + sa * tc::kTileBytes + ks * tc::kSlabBytes, 128),
+                                         umma::smem_desc(b0 + c * tc::kTileBytes + ks * tc::kSlabBytes, 128), idesc, ks > 0);
+                umma::commit_elect(&d_full[ds]);
+            }
+            umma::commit_elect(&a_empty[sa]);
+        }
+    } else if (warp == kTcThreads / 32 - 2) {
         if (lane == 0) {
-            // ---------------- MMA issuer (+ the one bulk copy of the codebook image) ----------------
+            // ---------------- bulk copies: the codebook image once, then the raw tiles, kTcRawSlots tiles ahead ----------------
             const uint32_t bytes = (uint32_t)tc_image_bytes(Kp);
             mbar_arrive_expect_tx(b_full, bytes);
             for (uint32_t off = 0; off < bytes; off += tc::kTileBytes)
                 bulk_g2s(sB + off, packed + 256 + off, tc::kTileBytes, b_full);
-            mbar_wait(b_full, 0);
-            const uint32_t idesc = tc::instr_desc_f16(128, 128);
-            const uint32_t a0 = smem_u32(sA), b0 = smem_u32(sB);
-            uint32_t u = 0;
-            for (long i = 0; i < my_tiles; ++i) {
-                const int sa = (int)(i % kTcASlots);
-                const uint32_t na = (uint32_t)(i / kTcASlots);
-                mbar_wait(&a_full[sa], na & 1u);
-                umma::fence_after_sync();
-                for (int c = 0; c < nchunks; ++c, ++u) {
-                    const int ds = (int)(u % kTcDSlots);
-                    const uint32_t nd = u / kTcDSlots;
-                    if (nd > 0) { mbar_wait(&d_empty[ds], (nd - 1) & 1u); umma::fence_after_sync(); }
-#pragma unroll
-                    for (int ks = 0; ks < 4; ++ks)
-                        tc::mma_f16(tb + (uint32_t)ds * 128u, umma::smem_desc(a0 + sa * tc::kTileBytes + ks * tc::kSlabBytes, 128),
-                                    umma::smem_desc(b0 + c * tc::kTileBytes + ks * tc::kSlabBytes, 128), idesc, ks > 0);
-                    umma::commit(&d_full[ds]);
-                }
-                umma::commit(&a_empty[sa]);
-            }
-        } else if (lane == 1) {
-            // ---------------- raw-tile producer: HBM -> shared memory, kTcRawSlots tiles ahead ----------------
             for (long i = 0; i < my_tiles; ++i) {
                 const int sr = (int)(i % kTcRawSlots);
                 const uint32_t nr = (uint32_t)(i / kTcRawSlots);

@@ -186,11 +186,12 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
     unsigned char *sA = smem + tc_image_bytes(Kp);
     float *raw = reinterpret_cast<float *>(sA + kTcASlots * tc::kTileBytes);       // [kTcRawSlots][128][17] fp32, as in HBM
     float *pm = raw + kTcRawSlots * kTcRawFloats;                                   // [3][128][4]: best, second, column of column quarters 1..3
-    int *dec = reinterpret_cast<int *>(pm + 3 * 128 * 4);                               // [128] decided centroid (or -1)
-    uint64_t *bars = reinterpret_cast<uint64_t *>(dec + 128);
+    int *dec = reinterpret_cast<int *>(pm + 3 * 128 * 4);                               // [2][128] decided centroid (or -1), two tiles
+    uint64_t *bars = reinterpret_cast<uint64_t *>(dec + 2 * 128);
     uint64_t *b_full = bars, *a_full = bars + 1, *a_empty = a_full + kTcASlots, *d_full = a_empty + kTcASlots,
-             *d_empty = d_full + kTcDSlots, *raw_full = d_empty + kTcDSlots, *raw_empty = raw_full + kTcRawSlots;
-    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(raw_empty + kTcRawSlots);
+             *d_empty = d_full + kTcDSlots, *raw_full = d_empty + kTcDSlots, *raw_empty = raw_full + kTcRawSlots,
+             *dec_full = raw_empty + kTcRawSlots, *dec_empty = dec_full + 2;
+    uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(dec_empty + 2);
 
     const int tid = threadIdx.x, warp = __shfl_sync(0xffffffffu, tid >> 5, 0), lane = tid & 31;      // (warp index known to be uniform)
     const long my_tiles = ntiles > (long)blockIdx.x ? (ntiles - 1 - blockIdx.x) / gridDim.x + 1 : 0;
@@ -200,6 +201,7 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
         for (int s = 0; s < kTcASlots; ++s) { mbar_init(&a_full[s], kTcLoad / 32); mbar_init(&a_empty[s], 1); }
         for (int s = 0; s < kTcDSlots; ++s) { mbar_init(&d_full[s], 1); mbar_init(&d_empty[s], kTcScan / 32); }
         for (int s = 0; s < kTcRawSlots; ++s) { mbar_init(&raw_full[s], 1); mbar_init(&raw_empty[s], (kTcScan + kTcLoad) / 32); }
+        for (int s = 0; s < 2; ++s) { mbar_init(&dec_full[s], kTcScan / 32); mbar_init(&dec_empty[s], kTcLoad / 32); }
         mbar_fence_init();
     }
     if (warp == 0) umma::tmem_alloc(tmem_slot, 512);
@@ -265,6 +267,39 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
         // ---------------- loaders: vectors -> fp16-pair A tiles ----------------
         const int r0 = tid - kTcScan;
         const __half one = __float2half_rn(1.0f);
+        // The loaders also add the vectors of a DECIDED tile to the sums (cb_func.py:82-86), one tile behind their
+        // conversions: 2 304 float64 atomics per tile, which the L2 takes at about one per cycle and SM -- done by the
+        // scanning warps they were 27 % of a tile; here they run beside the scan of the next tile.
+        auto accumulate = [&](long i) {
+            const int sr = (int)(i % kTcRawSlots), sd = (int)(i & 1);
+            const long t = tile_index(i);
+            mbar_wait(&dec_full[sd], (uint32_t)(i >> 1) & 1u);
+            for (int r = r0; r < 128; r += kTcLoad) {
+                const int b = dec[sd * 128 + r];
+                if (b >= 0) {
+                    float x[kDim];
+                    if (tile_is_bulk(t)) {
+#pragma unroll
+                        for (int d = 0; d < kDim; ++d) x[d] = raw[sr * kTcRawFloats + r * kDim + d];
+                    } else {
+#pragma unroll
+                        for (int d = 0; d < kDim; ++d) x[d] = __ldg(data + (t * 128 + r) * kDim + d);
+                    }
+                    double *s2 = sums, *c2 = counts;
+                    if (R > 1) {
+                        const int rep = (int)(((long)blockIdx.x * 128 + r) % R);
+                        s2 += (size_t)rep * K * kDim;
+                        c2 += (size_t)rep * K;
+                    }
+                    s2 += (size_t)b * kDim;
+#pragma unroll
+                    for (int d = 0; d < kDim; ++d) atomicAdd(s2 + d, (double)x[d]);
+                    atomicAdd(c2 + b, 1.0);
+                }
+            }
+            __syncwarp();
+            if (lane == 0) { mbar_arrive(&dec_empty[sd]); mbar_arrive(&raw_empty[sr]); }
+        };
         for (long i = 0; i < my_tiles; ++i) {
             const int sa = (int)(i % kTcASlots), sr = (int)(i % kTcRawSlots);
             const uint32_t na = (uint32_t)(i / kTcASlots);
@@ -292,8 +327,13 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
             }
             umma::fence_async_smem();
             __syncwarp();
-            if (lane == 0) { mbar_arrive(&raw_empty[sr]); mbar_arrive(&a_full[sa]); }
+            if (lane == 0) {
+                mbar_arrive(&a_full[sa]);
+                if (!sums) mbar_arrive(&raw_empty[sr]);          // (with sums the slot is released after its accumulation)
+            }
+            if (sums && i > 0) accumulate(i - 1);
         }
+        if (sums && my_tiles > 0) accumulate(my_tiles - 1);
     } else {
         // ---------------- scanners ----------------
         const int q = warp & 3, cq = warp >> 2;
@@ -397,32 +437,19 @@ kmeans_assign_tc_kernel(const float *__restrict__ data, long N, const double *__
                     const int bk = tc_exact_assign(data + (row - lane + src) * kDim, __shfl_sync(0xffffffffu, rr2, src), beta, K, sB, cb, lane);
                     if (lane == src) b = bk;
                 }
-                dec[r] = valid ? b : -1;
+                if (sums) {
+                    if (i >= 2) mbar_wait(&dec_empty[i & 1], (uint32_t)((i >> 1) - 1) & 1u);     // the loaders are done with tile i - 2
+                    dec[(i & 1) * 128 + r] = valid ? b : -1;
+                }
                 if (valid && idx_out) idx_out[row] = b;
             }
             TCP(4);
-            named_bar_sync(1, kTcScan);
-            TCP(5);
-            // sums and counts (cb_func.py:82-86): float64 atomics, the 17 dimensions split between the four warps of a row
             if (sums) {
-                const int b = dec[r];
-                if (b >= 0) {
-                    double *s2 = sums;
-                    double *c2 = counts;
-                    if (R > 1) {
-                        const int rep = (int)(((long)blockIdx.x * 128 + r) % R);
-                        s2 += (size_t)rep * K * kDim;
-                        c2 += (size_t)rep * K;
-                    }
-                    s2 += (size_t)b * kDim;
-                    // the 17 dimensions (+ the count) are split between the warps that share the row
-                    const int d0 = cq * 18 / kTcColParts, d1 = (cq + 1) * 18 / kTcColParts;
-#pragma unroll
-                    for (int d = 0; d < kDim; ++d)
-                        if (d >= d0 && d < d1) atomicAdd(s2 + d, (double)x[d]);
-                    if (d1 == 18) atomicAdd(c2 + b, 1.0);
-                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(&dec_full[i & 1]);        // all eight scanning warps arrive (four of them wrote)
             }
+            named_bar_sync(1, kTcScan);          // the partial minima of this tile have been read: the next scan may overwrite them
+            TCP(5);
             TCP(6);
         }
 #ifdef FPC_KMEANS_TC_PROF
@@ -442,7 +469,7 @@ size_t kmeans_tc_smem_bytes(int K)
 {
     const int Kp = (K + 127) / 128 * 128;
     return tc_image_bytes(Kp) + (size_t)kTcASlots * tc::kTileBytes + (size_t)kTcRawSlots * kTcRawFloats * 4 + 3 * 128 * 4 * 4 + 128 * 4 +
-           (1 + 2 * kTcASlots + 2 * kTcDSlots + 2 * kTcRawSlots) * 8 + 16;
+           128 * 4 + (1 + 2 * kTcASlots + 2 * kTcDSlots + 2 * kTcRawSlots + 4) * 8 + 16;
 }
 
 int num_sms();

@@ -639,7 +639,7 @@ def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
         kp = (K + 127) // 128 * 128
         res["K%d" % K] = {"iters_per_s": 1e3 / ms, "ms_per_iter": ms, "gpu_launches": int(fpc_native.launch_count() - n0),
                           "roofline": {"bound": "tensor", "kernel": "fpc::kmeans_assign_tc_kernel",
-                                       "what": "distance screen as a tcgen05 GEMM (vectors x centroids, fp16-pair operands, K = 64)",
+                                       "what": "distance screen as a tcgen05 GEMM (vectors x centroids, fp16-pair operands, K = 64); ncu (profiles/r2_kmeans_tc_ncu_raw.txt): tensor pipe 33 % active, the ALU pipe of the accumulator scan 67 % -- that is the pipe that binds",
                                        "achieved": 2.0 * n_total / world * K * 17 / (ms * 1e-3) / 1e12, "peak": pk["bf16_tflops_sustained"],
                                        "unit": "TFLOP/s", "frac": 2.0 * n_total / world * K * 17 / (ms * 1e-3) / 1e12 / pk["bf16_tflops_sustained"],
                                        "per": "GPU (the iteration includes the all-reduce and the finalize)",
@@ -763,7 +763,7 @@ def bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, 
                          "frac": per_gpu * (F_GRU + fq) / 1e12 / pk["bf16_tflops_sustained"], "flop_per_frame": F_GRU + fq,
                          "executed_mma_flop_per_frame": F_GRU + 16 * 4 * (1 + 3) * 262144.0 / 64 * p2,
                          "executed_tflops": per_gpu * (F_GRU + 16 * 4 * (1 + 3) * 262144.0 / 64 * p2) / 1e12,
-                         "ncu": "profiles/r2_encode_bf16_ncu_raw.txt: tensor pipe 11.6 % active, ALU pipe 24.6 %"},
+                         "ncu": "profiles/r2_encode_bf16_ncu_raw.txt: tensor pipe 12.5 % active, ALU pipe 24.5 %"},
             "fp32_equivalent": {"what": "round-1 yardstick: the quantiser's direct-form FLOPs against the FP32 pipe it used to run on",
                                 "achieved": per_gpu * fq / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                                 "frac": per_gpu * fq / 1e12 / fp32_peak, "flop_per_frame": fq},

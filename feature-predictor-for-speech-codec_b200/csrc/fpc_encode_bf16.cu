@@ -122,7 +122,7 @@ template <int NU> struct SmemB {
     // misc: m1[NU] m2[NU] (float), idx0/idx1/idx2[NU], listA[NU], listB[NU] (int), counts[4], tmem base, pad
     static constexpr int offScl = ((offMisc + (7 * NU + 8) * 4 + 15) / 16) * 16;      // both scalar tables, file dtype, 2 x 2 KB + {n, dtype} x 2
     static constexpr int offBars = offScl + 2 * FPC_MAX_SCL_ENTRIES * 8 + 16;
-    static constexpr int kNumBars = 2 * kBStages + 4;
+    static constexpr int kNumBars = 2 * kBStages + 6;
     static constexpr int kBase = ((offBars + kNumBars * 8 + 127) / 128) * 128;
     static constexpr int kScratchBytes = kX1Bytes;   // the dead [x | h1] tile doubles as VQ scratch
     // Tensor-core VQ screen (fpc_vq_tc.cuh).  The A tiles live in the scratch when they fit (64-utterance tiles: 3 x 16 KB
@@ -228,9 +228,9 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     uint32_t *tmem_slot = reinterpret_cast<uint32_t *>(counts + 4);
     uint64_t *full = reinterpret_cast<uint64_t *>(smem + S::offBars);
     uint64_t *empty = full + kBStages;
-    uint64_t *acc_full = empty + kBStages;
-    uint64_t *acc_empty = acc_full + 1;
-    uint64_t *act_ready = acc_empty + 1;
+    uint64_t *acc_full = empty + kBStages;     // [2]: the gate accumulators are double-buffered in tensor memory (4 NU columns
+    uint64_t *acc_empty = acc_full + 2;        // [2]   each): the MMAs of pass p + 1 run under the gate epilogue of pass p
+    uint64_t *act_ready = acc_empty + 2;
     uint64_t *vq_done = act_ready + 1;        // compute warps -> weight producer: the screen no longer uses the weight ring
 
     const int tid = threadIdx.x;
@@ -244,8 +244,7 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
     static_assert(sizeof(VqTcShared<S::kNBTotal>) <= 512, "control block");
     if (tid == 0) {
         for (int s = 0; s < kBStages; ++s) { mbar_init(&full[s], 1); mbar_init(&empty[s], 3); }      // three issuing warps
-        mbar_init(acc_full, 3);
-        mbar_init(acc_empty, kComputeThreads / 32);
+        for (int b = 0; b < 2; ++b) { mbar_init(&acc_full[b], 3); mbar_init(&acc_empty[b], kComputeThreads / 32); }
         mbar_init(act_ready, kComputeThreads / 32);
         mbar_init(vq_done, 1);
         vq_tc_init<S::kNBTotal>(vsh, kComputeThreads / 32);
@@ -317,7 +316,8 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                     // ---- GRU 1: three passes of 128 hidden units ----
                     mbar_wait(act_ready, n_act & 1u); ++n_act;
                     for (int pass = 0; pass < 3; ++pass) {
-                        mbar_wait(acc_empty, (n_acc & 1u) ^ 1u); ++n_acc;
+                        const uint32_t ab = n_acc & 1u, tacc = tb + ab * (4 * NU);      // accumulator buffer of this pass
+                        mbar_wait(&acc_empty[ab], ((n_acc >> 1) & 1u) ^ 1u); ++n_acc;
                         umma::fence_after_sync();
                         for (int i = 0; i < kBG1Steps; ++i) {
                             mbar_wait(&full[s], ph);
@@ -326,15 +326,16 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                             const uint64_t bd = umma::smem_desc(x1a0 + (uint32_t)cur * S::kX1Bytes + (uint32_t)(2 * i) * (NU * 16), NU);
                             // gates r, z: one accumulator over x and h; gate n: n_i over the two x steps, n_h over the h steps
                             const bool nh = gate == 2 && i >= 2;
-                            umma::mma_bf16_elect(tb + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > 2 : i > 0);
+                            umma::mma_bf16_elect(tacc + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > 2 : i > 0);
                             umma::commit_elect(&empty[s]);
                             if (++s == kBStages) { s = 0; ph ^= 1u; }
                         }
-                        umma::commit_elect(acc_full);
+                        umma::commit_elect(&acc_full[ab]);
                     }
                     // ---- GRU 2: input h1' (the other [x | h1] tile), hidden h2 ----
                     mbar_wait(act_ready, n_act & 1u); ++n_act;
-                    mbar_wait(acc_empty, (n_acc & 1u) ^ 1u); ++n_acc;
+                    const uint32_t ab = n_acc & 1u, tacc = tb + ab * (4 * NU);
+                    mbar_wait(&acc_empty[ab], ((n_acc >> 1) & 1u) ^ 1u); ++n_acc;
                     umma::fence_after_sync();
                     for (int i = 0; i < kBG2Steps; ++i) {
                         mbar_wait(&full[s], ph);
@@ -345,11 +346,11 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
                                                   : h2a + (uint32_t)(2 * (i - kH1 / 16)) * (NU * 16);
                         const uint64_t bd = umma::smem_desc(baddr, NU);
                         const bool nh = gate == 2 && !xp;
-                        umma::mma_bf16_elect(tb + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > kH1 / 16 : i > 0);
+                        umma::mma_bf16_elect(tacc + (uint32_t)((nh ? 3 : gate) * NU), umma::smem_desc(a0, 128), bd, idesc, nh ? i > kH1 / 16 : i > 0);
                         umma::commit_elect(&empty[s]);
                         if (++s == kBStages) { s = 0; ph ^= 1u; }
                     }
-                    umma::commit_elect(acc_full);
+                    umma::commit_elect(&acc_full[ab]);
                     cur ^= 1;
                     // the searches of this frame: stages of the codebooks as published by the compute warps
                     if (P.mode == kModeQuantize && gate != 1) {      // warps 9 and 11 issue alternate chunks
@@ -426,24 +427,26 @@ __global__ void __launch_bounds__(kBThreads, 1) encode_bf16_kernel(EncodeParams 
             // ---- GRU 1 (wavernn.py:71): gate epilogues of the three passes ----
 #pragma unroll 1
             for (int pass = 0; pass < 3; ++pass) {
-                mbar_wait(acc_full, n_full & 1u); ++n_full;
+                const uint32_t ab = n_full & 1u;
+                mbar_wait(&acc_full[ab], (n_full >> 1) & 1u); ++n_full;
                 umma::fence_after_sync();
-                gate_epilogue<NU>(tb, q, hsel, lane, bias + pass * 512, x1[cur], x1[cur ^ 1], 32 + pass * 128);
+                gate_epilogue<NU>(tb + ab * (4 * NU), q, hsel, lane, bias + pass * 512, x1[cur], x1[cur ^ 1], 32 + pass * 128);
                 umma::fence_before_sync();
                 if (pass == 2) umma::fence_async_smem();     // h1' is the B operand of GRU 2
                 __syncwarp();
                 if (lane == 0) {
-                    mbar_arrive(acc_empty);
+                    mbar_arrive(&acc_empty[ab]);
                     if (pass == 2) mbar_arrive(act_ready);
                 }
             }
             // ---- GRU 2 (wavernn.py:76), state updated in place ----
-            mbar_wait(acc_full, n_full & 1u); ++n_full;
+            const uint32_t ab2 = n_full & 1u;
+            mbar_wait(&acc_full[ab2], (n_full >> 1) & 1u); ++n_full;
             umma::fence_after_sync();
-            gate_epilogue<NU>(tb, q, hsel, lane, bias + 3 * 512, h2t, h2t, 0);
+            gate_epilogue<NU>(tb + ab2 * (4 * NU), q, hsel, lane, bias + 3 * 512, h2t, h2t, 0);
             umma::fence_before_sync();
             __syncwarp();
-            if (lane == 0) mbar_arrive(acc_empty);
+            if (lane == 0) mbar_arrive(&acc_empty[ab2]);
             named_bar_sync(1, kComputeThreads);
 
             FPC_PHASE(kPhGru);

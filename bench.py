@@ -763,7 +763,7 @@ def bench_bf16(args, torch, dist, dev, rank, world, barrier, model, cfg, S, l1, 
                          "frac": per_gpu * (F_GRU + fq) / 1e12 / pk["bf16_tflops_sustained"], "flop_per_frame": F_GRU + fq,
                          "executed_mma_flop_per_frame": F_GRU + 16 * 4 * (1 + 3) * 262144.0 / 64 * p2,
                          "executed_tflops": per_gpu * (F_GRU + 16 * 4 * (1 + 3) * 262144.0 / 64 * p2) / 1e12,
-                         "ncu": "profiles/r2_encode_bf16_ncu_raw.txt: tensor pipe 12.5 % active, ALU pipe 24.5 %"},
+                         "ncu": "profiles/r2_encode_bf16_ncu_raw.txt: tensor pipe 13.0 % active, ALU pipe 25.5 %"},
             "fp32_equivalent": {"what": "round-1 yardstick: the quantiser's direct-form FLOPs against the FP32 pipe it used to run on",
                                 "achieved": per_gpu * fq / 1e12, "peak": fp32_peak, "unit": "TFLOP/s",
                                 "frac": per_gpu * fq / 1e12 / fp32_peak, "flop_per_frame": fq},

@@ -40,10 +40,7 @@
 
 namespace fpc {
 
-#ifndef FPC_STAGES
-#define FPC_STAGES 4
-#endif
-constexpr int kStages = FPC_STAGES;             // weight ring depth
+constexpr int kStages = 4;             // weight ring depth
 static_assert(kStages <= 8, "h1 is updated in place: a GEMM warp may run at most kStages groups ahead of the slowest");
 constexpr int kTailThreads = 128;
 constexpr int kThreads = kComputeThreads + kTailThreads + 128;   // 2 GEMM warpgroups + tail warpgroup + helper warpgroup
@@ -166,21 +163,15 @@ template <> struct TmIo<16> {
 template <int N> __device__ __forceinline__ void tmem_st_n(uint32_t ta, const uint32_t *r)
 {
     static_assert(N >= 0 && N % 2 == 0, "even column counts");
-#ifndef FPC_TMEM_MAX8
     if constexpr (N >= 16) { TmIo<16>::st(ta, r); tmem_st_n<N - 16>(ta + 16, r + 16); }
-    else
-#endif
-    if constexpr (N >= 8) { TmIo<8>::st(ta, r); tmem_st_n<N - 8>(ta + 8, r + 8); }
+    else if constexpr (N >= 8) { TmIo<8>::st(ta, r); tmem_st_n<N - 8>(ta + 8, r + 8); }
     else if constexpr (N >= 4) { TmIo<4>::st(ta, r); tmem_st_n<N - 4>(ta + 4, r + 4); }
     else if constexpr (N >= 2) { TmIo<2>::st(ta, r); }
 }
 template <int N> __device__ __forceinline__ void tmem_ld_n(uint32_t ta, uint32_t *r)
 {
-#ifndef FPC_TMEM_MAX8
     if constexpr (N >= 16) { TmIo<16>::ld(ta, r); tmem_ld_n<N - 16>(ta + 16, r + 16); }
-    else
-#endif
-    if constexpr (N >= 8) { TmIo<8>::ld(ta, r); tmem_ld_n<N - 8>(ta + 8, r + 8); }
+    else if constexpr (N >= 8) { TmIo<8>::ld(ta, r); tmem_ld_n<N - 8>(ta + 8, r + 8); }
     else if constexpr (N >= 4) { TmIo<4>::ld(ta, r); tmem_ld_n<N - 4>(ta + 4, r + 4); }
     else if constexpr (N >= 2) { TmIo<2>::ld(ta, r); }
 }

@@ -224,6 +224,26 @@ def test_encode_host_matches_device_path(torch_cuda, model, synth, cbdir, B, L, 
         model.encode_host(cfg, fh.cuda(), 0.25, 2.1)
 
 
+@pytest.mark.parametrize("height", [28, 32])
+def test_encode_host_under_full_load(torch_cuda, model, synth, cbdir, height, monkeypatch):
+    """The time-chunked host path with every SM busy and an odd number of frames per launch (the carried state then sits
+    in the second h2 buffer at a launch boundary): identical to the device-resident call, for both tile heights the
+    launch plan uses for large batches."""
+    torch = torch_cuda
+    sms = torch.cuda.get_device_properties(0).multi_processor_count
+    B, L = sms * height + 5, 35
+    cfg = synth.save_codebooks(synth.make_codebooks(0), os.path.join(cbdir, "hostload%d" % height))
+    base = synth.make_features(96, L, first_utt=9500)
+    feat = np.ascontiguousarray(np.tile(base, ((B + 95) // 96, 1, 1))[:B])
+    monkeypatch.setenv("FPC_FP32_TILE", str(height))
+    ref = run_gpu(torch, model, cfg, feat, 0.25, 2.1)
+    host = model.encode_host(cfg, torch.from_numpy(feat).pin_memory(), 0.25, 2.1, chunks=5)       # 7 frames per launch
+    torch.cuda.synchronize()
+    monkeypatch.delenv("FPC_FP32_TILE")
+    for k in ("c_in", "r", "r_qtz", "ind1", "ind2", "idx"):
+        assert np.array_equal(host[k].numpy(), ref[k]), (k, height)
+
+
 def test_residual_mode_and_masks(torch_cuda, model, oracle, oracle_weights, synth):
     feat = synth.make_features(19, 30, first_utt=7100)
     gpu = run_gpu(torch_cuda, model, {}, feat, 0.25, 2.1, qtz=False)

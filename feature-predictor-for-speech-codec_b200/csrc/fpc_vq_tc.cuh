@@ -158,27 +158,24 @@ __device__ __forceinline__ bool vq_tc_issue_phase(VqTcShared<NB, UNITS> *sh, uin
         const int bs = (int)(n.b % NB);
         mbar_wait(&sh->b_full[bs], (n.b / NB) & 1u);
         FPC_VQ_TRACE(64);
+        umma::fence_after_sync();
+        FPC_VQ_TRACE(192);
+        const uint64_t bd = umma::smem_desc(vq_tc_slot_addr(bring_addr, ring2, bs), 64);
+        // tile by tile, each tile's four K = 16 slabs back to back and its commit right behind them: a dependent chain of
+        // MMAs into one accumulator costs nothing (tools/ubench_umma.cu: 48 cycles per MMA either way), and the first
+        // tile of a chunk is handed to the scanning warps while the tensor pipe still works on the others
 #pragma unroll
         for (int m = 0; m < 3; ++m)
             if (m < mtiles) {
                 const uint32_t use = (n.u + m) / UNITS;
-                if (use > 0) mbar_wait(&sh->d_empty[(n.u + m) % UNITS], (use - 1) & 1u);
-            }
-        umma::fence_after_sync();
-        FPC_VQ_TRACE(192);
-        const uint64_t bd = umma::smem_desc(vq_tc_slot_addr(bring_addr, ring2, bs), 64);
+                if (use > 0) { mbar_wait(&sh->d_empty[(n.u + m) % UNITS], (use - 1) & 1u); umma::fence_after_sync(); }
 #pragma unroll
-        for (int ks = 0; ks < 4; ++ks) {
-#pragma unroll
-            for (int m = 0; m < 3; ++m)
-                if (m < mtiles)
+                for (int ks = 0; ks < 4; ++ks)
                     umma::mma_bf16_elect(tb + ((n.u + m) % UNITS) * 64u, adesc0 + (uint64_t)((m * tc::kTileBytes + ks * tc::kSlabBytes) >> 4),
                                          bd + (uint64_t)((ks * kVtSlabBytes) >> 4), idesc, ks > 0);
-        }
+                umma::commit_elect(&sh->d_full[(n.u + m) % UNITS]);
+            }
         FPC_VQ_TRACE(320);
-#pragma unroll
-        for (int m = 0; m < 3; ++m)
-            if (m < mtiles) umma::commit_elect(&sh->d_full[(n.u + m) % UNITS]);
         umma::commit_elect(&sh->b_empty[bs]);
         FPC_VQ_TRACE(128);
         n.u += mtiles;

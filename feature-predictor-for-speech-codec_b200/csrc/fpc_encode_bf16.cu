@@ -24,6 +24,7 @@
 #include "fpc_vq.cuh"
 #include "fpc_vq_search.cuh"
 #include "fpc_vq_screen.cuh"
+#define FPC_VQ_TC_OUTLINE __forceinline__      // the search inlined: it then gets the compute warps' 216 registers (out of line: the launch allocation, 168)
 #include "fpc_vq_tc.cuh"
 #include "fpc_encode.cuh"
 #include "fpc_umma.cuh"

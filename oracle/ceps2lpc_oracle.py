@@ -79,3 +79,48 @@ def ceps2lpc(cepstrum):
         lpc[l] = lp
         err[l] = error
     return lpc, err, rc
+
+
+def ceps2lpc_f64(cepstrum):
+    """The same algorithm evaluated in float64 from the float32 input -- a GROUND TRUTH for judging float32 results
+    against one another (the reference's torch float32 evaluation, this file's float32 restatement, the CUDA kernel):
+    no float32 evaluation order is "the" right one, and the Levinson recursion amplifies their 1e-7 differences to
+    1e-3 in the coefficients.  Table constants are the reference's float32 ones (the DCT table and the compensation
+    gains are float32 tensors there, ceps2lpc_vct.py:16-33); the early exits (:82-85) are taken on the float64 error.
+    -> lpc (N,16), error (N,), rc (N,16), all float64."""
+    c = np.asarray(cepstrum, dtype=np.float32)[:, :NB_BANDS].astype(np.float64)
+    c[:, 0] += 4.0
+    D = dct_table().astype(np.float64)
+    ex = (c @ D.T) * float(np.sqrt(np.float32(2. / NB_BANDS)))
+    ex = np.power(10.0, ex) * COMPENSATION.astype(np.float64)
+    n = len(c)
+    g = np.zeros((n, FREQ_SIZE))
+    for i in range(NB_BANDS - 1):
+        bs = (EBAND5MS[i + 1] - EBAND5MS[i]) * WINDOW_SIZE_5MS
+        for j in range(bs):
+            frac = float(j) / bs
+            g[:, EBAND5MS[i] * WINDOW_SIZE_5MS + j] = (1 - frac) * ex[:, i] + frac * ex[:, i + 1]
+    acr = np.fft.irfft(g, n=WINDOW_SIZE, axis=1)[:, :LPC_ORDER + 1]
+    acr[:, 0] += acr[:, 0] * float(np.float32(0.0001)) + float(np.float32(320 / 12 / 38.))
+    for i in range(1, LPC_ORDER + 1):
+        acr[:, i] *= 1 - 0.00006 * i * i
+    lpc = np.zeros((n, LPC_ORDER))
+    err = np.zeros(n)
+    rc = np.zeros((n, LPC_ORDER))
+    for l in range(n):
+        ac = acr[l]
+        error = ac[0]
+        lp = np.zeros(LPC_ORDER)
+        if ac[0] != 0:
+            for i in range(LPC_ORDER):
+                r = -(np.dot(lp[:i], ac[i:0:-1]) + ac[i + 1]) / error
+                rc[l, i] = r
+                head = lp[:i].copy()
+                lp[:i] = head + r * head[::-1]
+                lp[i] = r
+                error = error - r * r * error
+                if error < ac[0] / 2 ** 10 or error < 0.001 * ac[0]:
+                    break
+        lpc[l] = lp
+        err[l] = error
+    return lpc, err, rc

@@ -10,7 +10,7 @@
 // (bin 160 is never written by the interpolation, :49-56) collapse to an 18 x 17 float64 table T[b][n] built from
 // the reference's float32 interpolation weights:  acr[n] = sum_b E[b] T[b][n], 306 float64 FMAs per frame instead of
 // 2 703.  That skips the reference's float32 rounding of every X_k (and torch's float32 FFT): against a float64
-// evaluation of the whole algorithm (oracle/ceps2lpc_oracle.py: ceps2lpc_f64) the result is CLOSER than the
+// evaluation of the whole algorithm (the test suite's ceps2lpc_f64 ground truth) the result is CLOSER than the
 // reference's own (tests/test_ceps2lpc_bitrate.py).  Everything else is float32 in the reference's operation order,
 // including the two early exits of the Levinson recursion.  The recursion is ill-conditioned (1e-4 noise floor), so
 // LPC parity is a stated tolerance, not bit-exact.

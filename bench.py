@@ -648,6 +648,23 @@ def bench_kmeans(args, torch, dist, dev, rank, world, barrier):
                           "fp32_direct_form_tflops": flops / (ms * 1e-3) / 1e12,
                           "hbm_gbs": n_total * 68.0 / world / (ms * 1e-3) / 1e9,
                           "empty_clusters": float(stats[2].item()), "vectors_seen": int(n_seen)}
+        if K == 1024:
+            # opt-in exact mode: sums in data order like cb_func.py:82-86 (fpc_kmeans_accumulate_ordered) -- the codebook
+            # of the reference bit for bit on one GPU; a stable counting sort of the rows + one warp per centroid
+            co = cb
+            for _ in range(2):
+                co, _, _ = cb_func.update_device(data, co, ordered=True)
+            barrier()
+            e0.record(stream)
+            for _ in range(iters):
+                co, _, _ = cb_func.update_device(data, co, ordered=True)
+            e1.record(stream)
+            barrier()
+            t = torch.tensor([e0.elapsed_time(e1)], dtype=torch.float64, device=dev)
+            if world > 1:
+                dist.all_reduce(t, op=dist.ReduceOp.MAX)
+            res["K1024"]["ordered_sums"] = {"ms_per_iter": float(t.item()) / iters, "iters_per_s": 1e3 * iters / float(t.item()),
+                                            "what": "update_device(ordered=True): index-only assignment + sums in data order (bit-exact vs the reference on one GPU)"}
     res["vectors"] = n_total
     res["sharding"] = "%d vectors per rank, all-reduce of (K,17) sums + (K) counts per iteration" % data.shape[0]
     res["scaling"] = "strong"

@@ -13,7 +13,7 @@ import sys
 
 HERE = os.path.dirname(os.path.abspath(__file__))
 LIB = os.path.join(HERE, "libfpc_b200.so")
-SRCS = ["fpc_pack.cu", "fpc_encode_fp32.cu", "fpc_api.cu", "fpc_kmeans.cu", "fpc_kmeans_tc.cu", "fpc_umma_selftest.cu", "fpc_encode_bf16.cu", "fpc_ceps2lpc.cu", "fpc_train.cu"]
+SRCS = ["fpc_pack.cu", "fpc_encode_fp32.cu", "fpc_api.cu", "fpc_kmeans.cu", "fpc_kmeans_tc.cu", "fpc_kmeans_ordered.cu", "fpc_umma_selftest.cu", "fpc_encode_bf16.cu", "fpc_ceps2lpc.cu", "fpc_train.cu"]
 NVCC = os.environ.get("NVCC", "/usr/local/cuda/bin/nvcc")
 FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-std=c++17", "-lineinfo", "-fmad=false",
          "-Xcompiler", "-fPIC", "-Xcompiler", "-fvisibility=hidden"]

@@ -24,7 +24,7 @@ EXPORTS = (
     "fpc_decode", "fpc_index_histogram",
     "fpc_vq_quantize_packed", "fpc_scl_quantize",
     "fpc_kmeans_workspace_bytes", "fpc_kmeans_assign_accumulate", "fpc_kmeans_finalize", "fpc_kmeans_finalize_acc", "fpc_kmeans_colsum_f32", "fpc_kmeans_colsum_f64", "fpc_kmeans_assign_accumulate_f64",
-    "fpc_kmeans_stage_residual_f64", "fpc_kmeans_gather",
+    "fpc_kmeans_stage_residual_f64", "fpc_kmeans_gather", "fpc_kmeans_ordered_workspace_bytes", "fpc_kmeans_accumulate_ordered",
     "fpc_selftest_umma", "fpc_selftest_tc_scores", "fpc_debug_set_phase_buffer", "fpc_ceps2lpc",
     "fpc_compact_workspace_bytes", "fpc_compact_rows", "fpc_kmeans_stage_residual",
     "fpc_dequantize", "fpc_pack_frames", "fpc_unpack_frames",
@@ -137,6 +137,9 @@ def lib():
     L.fpc_kmeans_assign_accumulate_f64.argtypes = L.fpc_kmeans_assign_accumulate.argtypes
     L.fpc_kmeans_stage_residual_f64.argtypes = [vp, ci, vp, vp, ci, cl, vp, vp]
     L.fpc_kmeans_gather.argtypes = [vp, ci, vp, cl, vp, vp]
+    L.fpc_kmeans_ordered_workspace_bytes.restype = cs
+    L.fpc_kmeans_ordered_workspace_bytes.argtypes = [cl, ci]
+    L.fpc_kmeans_accumulate_ordered.argtypes = [vp, ci, cl, vp, ci, vp, vp, vp, cs, vp]
     L.fpc_selftest_umma.argtypes = [vp, vp, ci, ci, vp, vp]
     L.fpc_selftest_tc_scores.argtypes = [vp, ci, vp, ci, vp, vp, vp]
     L.fpc_debug_set_phase_buffer.argtypes = [vp]

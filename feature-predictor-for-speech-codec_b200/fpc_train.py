@@ -78,20 +78,21 @@ def stage_residual(codebook, data, keep_float64=True):
     return nxt
 
 
-def train_stages(data, n_entries, codebooks=None, first_batch=True, group=None, rng=None, keep_float64=True):
+def train_stages(data, n_entries, codebooks=None, first_batch=True, group=None, rng=None, keep_float64=True, ordered=None):
     """train_cb.py:189-211 for one batch of residual vectors: for every stage, `vq_train` (first batch) or ten
     `update` calls (later batches), then the next stage trains on quantize(cb, r) - r.
+    ordered=True: sums in data order (cb_func.update_device), the reference's codebooks bit for bit on one GPU.
     Returns the list of (K_i, 17) float64 codebooks."""
     d = cb_func._data_on_device(data)
     out = []
     for i, K in enumerate(n_entries):
         cb0 = np.zeros((K, 17)) if codebooks is None else np.asarray(codebooks[i], dtype=np.float64)
         if first_batch:
-            cb = cb_func.vq_train(d, cb0, K, group=group, rng=rng)
+            cb = cb_func.vq_train(d, cb0, K, group=group, rng=rng, ordered=ordered)
         else:
             cb = cb0
             for _ in range(10):
-                cb = cb_func.update(d, cb, K, group=group, verbose=False)
+                cb = cb_func.update(d, cb, K, group=group, verbose=False, ordered=ordered)
         out.append(cb)
         if i + 1 < len(n_entries):
             d = stage_residual(cb, d, keep_float64)

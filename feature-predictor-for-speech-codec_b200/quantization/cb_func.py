@@ -15,7 +15,16 @@ rank's shard of the residual vectors; per-centroid float64 sums and counts are a
 (NCCL over NVLink) between the assign kernel and the divide, so every rank ends an iteration
 with the same codebook.  The jitter of vq_train comes from NumPy's global RNG exactly as in the
 reference (:41); with several ranks rank 0's draw is broadcast.
+
+`ordered=True` (update / update_device / vq_train; default from the environment variable FPC_KMEANS_ORDERED=1): the
+per-centroid sums are taken in DATA ORDER like the reference's accumulation loop (:82-86) by
+fpc_kmeans_accumulate_ordered, so that on one GPU `update` returns the reference's codebook BIT FOR BIT and the same
+bits on every run.  The default sums with float64 atomics inside the assign kernel: faster (one pass instead of five),
+equal to ~1e-16 relative per sum, not bit-reproducible.  With several ranks the ordered sums of the shards are still
+combined by the all-reduce, i.e. reproducible for a given rank count but not the one-GPU bits.
 """
+import os
+
 import numpy as np
 
 import fpc_dist
@@ -97,7 +106,26 @@ def _accumulator(dev, K, n):
     return hit
 
 
-def update_device(data_dev, cb_dev, group=None):
+def _ordered_default():
+    return os.environ.get("FPC_KMEANS_ORDERED", "0") not in ("", "0")
+
+
+_ord_cache = {}     # device -> [row indices (int32), workspace (uint8)] of the ordered accumulation
+
+
+def _ordered_scratch(dev, n, K):
+    torch = _torch()
+    need = N.lib().fpc_kmeans_ordered_workspace_bytes(n, K)
+    if need == 0 and n > 0:
+        raise ValueError("ordered accumulation needs K <= 2048 and fewer than 2^31 vectors (K = %d, N = %d)" % (K, n))
+    hit = _ord_cache.get(str(dev))
+    if hit is None or hit[0].numel() < n or hit[1].numel() < need:
+        hit = [torch.empty((max(n, 1),), dtype=torch.int32, device=dev), torch.empty(max(need, 1), dtype=torch.uint8, device=dev)]
+        _ord_cache[str(dev)] = hit
+    return hit
+
+
+def update_device(data_dev, cb_dev, group=None, ordered=None):
     """One Lloyd iteration entirely on the device (+ the all-reduce when distributed), no host synchronisation.
     Returns (new codebook (K,17) f64 device tensor, stats (5,) f64 device tensor = min count, max count, #empty,
     sum (count/N)^2, N; the global vector count N as a 0-d device tensor view of stats[4]).
@@ -113,11 +141,24 @@ def update_device(data_dev, cb_dev, group=None):
     acc, ws = _accumulator(dev, K, n)
     out = torch.empty((K, 17), dtype=torch.float64, device=dev)
     stats = torch.empty((5,), dtype=torch.float64, device=dev)
+    if ordered is None:
+        ordered = _ordered_default()
     try:
         with torch.cuda.device(dev):
-            N.check(_assign_fn(data_dev)(
-                data_dev.data_ptr(), n, cb_dev.data_ptr(), K, acc.data_ptr(), acc.data_ptr() + K * 17 * 8, None,
-                ws.data_ptr(), ws.numel(), N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
+            if ordered:
+                # indices only, then the sums in data order (cb_func.py:82-86 to the bit)
+                idx, ows = _ordered_scratch(dev, n, K)
+                N.check(_assign_fn(data_dev)(
+                    data_dev.data_ptr(), n, cb_dev.data_ptr(), K, None, None, idx.data_ptr(),
+                    ws.data_ptr(), ws.numel(), N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
+                N.check(N.lib().fpc_kmeans_accumulate_ordered(
+                    data_dev.data_ptr(), int(data_dev.dtype == torch.float64), n, idx.data_ptr(), K, acc.data_ptr(),
+                    acc.data_ptr() + K * 17 * 8, ows.data_ptr(), ows.numel(), N.current_stream(dev)),
+                    "fpc_kmeans_accumulate_ordered")
+            else:
+                N.check(_assign_fn(data_dev)(
+                    data_dev.data_ptr(), n, cb_dev.data_ptr(), K, acc.data_ptr(), acc.data_ptr() + K * 17 * 8, None,
+                    ws.data_ptr(), ws.numel(), N.current_stream(dev)), "fpc_kmeans_assign_accumulate")
             if fpc_dist.is_distributed(group):
                 fpc_dist._dist().all_reduce(acc, op=fpc_dist._dist().ReduceOp.SUM, group=group)
             # n_total = 0: nb_vectors is the sum of the (all-reduced) counts, taken on the device
@@ -140,11 +181,11 @@ def find_nearest(data, codebook):
     return idx.cpu().numpy().astype(np.int64)
 
 
-def update(data, codebook, nb_entries_tmp, group=None, verbose=True):
+def update(data, codebook, nb_entries_tmp, group=None, verbose=True, ordered=None):
     """cb_func.py:71-100.  Prints the same statistics line as the reference (:96-97)."""
     d = _data_on_device(data)
     cb = _cb_on_device(np.asarray(codebook)[:nb_entries_tmp], d.device)
-    out, stats, _ = update_device(d, cb, group)
+    out, stats, _ = update_device(d, cb, group, ordered)
     s = stats.cpu().numpy()
     if verbose and fpc_dist.rank(group) == 0:
         print('{} - min: {}, max: {}, small: {}, error: {}'.format(
@@ -167,7 +208,7 @@ def quantize(codebook, data):
     return q.cpu().numpy()
 
 
-def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
+def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None, ordered=None):
     """cb_func.py:28-54.  The residuals go to the device once and the codebook stays there for the whole schedule:
     each of the 4(K-1)+10 Lloyd iterations is one assign kernel, one (optional) all-reduce and one finalize kernel,
     and the grow-by-one step (copy entry 0, add the jitter) is two small device operations, so the host never waits
@@ -208,12 +249,12 @@ def vq_train(data, codebook, nb_entries, group=None, verbose=False, rng=None):
         off += e * ndims
         e += 1
         for _ in range(4):
-            cb, stats, _ = update_device(d, cb_full[:e], group)
+            cb, stats, _ = update_device(d, cb_full[:e], group, ordered)
             cb_full[:e] = cb
         if verbose and fpc_dist.rank(group) == 0:
             s = stats.cpu().numpy()
             print('{} - min: {}, max: {}, small: {}, error: {}'.format(e, s[0], s[1], int(s[2]), s[3]))
     cb = cb_full[:nb_entries]
     for _ in range(10):
-        cb, stats, _ = update_device(d, cb, group)
+        cb, stats, _ = update_device(d, cb, group, ordered)
     return cb.cpu().numpy()

@@ -18,6 +18,7 @@
  *   fpc_scl_quantize           <- quantization/vq_func.py:167-185  scl_quantize
  *   fpc_index_histogram        <- models/wavernn.py:189,221-240    cb_tot accumulation
  *   fpc_kmeans_assign_accumulate <- quantization/cb_func.py:56-68,82-86  find_nearest + sums
+ *   fpc_kmeans_accumulate_ordered <- quantization/cb_func.py:82-86  the same sums, in data order (bit-exact)
  *   fpc_kmeans_finalize        <- quantization/cb_func.py:88-97    divide, cluster statistics
  *   fpc_kmeans_gather          <- quantization/cb_func.py:103-112  quantize
  *   fpc_ceps2lpc               <- ceps2lpc/ceps2lpc_vct.py:122-162 ceps2lpc_v
@@ -267,6 +268,17 @@ int fpc_kmeans_assign_accumulate_f64(const double *d_data, long N, const double 
  * of the previous rank. */
 int fpc_kmeans_colsum_f32(const float *d_data, long N, float *d_carry, void *stream);
 int fpc_kmeans_colsum_f64(const double *d_data, long N, double *d_carry, void *stream);   /* float64 rows, float64 additions */
+/* The accumulation loop of cb_func.update IN DATA ORDER (cb_func.py:82-86: `count[n] += 1; sum[n] += data[i]` for
+ * i = 0, 1, ...): given the indices d_idx (N) that fpc_kmeans_assign_accumulate wrote, ADDS to d_sums (K,17) the
+ * vectors of each centroid one after the other in ascending row order, in float64, and their number to d_counts (K).
+ * Where the assign kernel's own sums (float64 atomics, scheduling order) match the reference to ~1e-16 relative, these
+ * match it bit for bit and are the same from run to run.  A stable counting sort of the row numbers by centroid plus
+ * one warp per centroid; K <= 2048, N < 2^31.  d_data: float32 rows, or float64 rows when data_is_f64.
+ * d_workspace: fpc_kmeans_ordered_workspace_bytes(N, K) bytes (row permutation + tile counts). */
+size_t fpc_kmeans_ordered_workspace_bytes(long N, int K);
+int fpc_kmeans_accumulate_ordered(const void *d_data, int data_is_f64, long N, const int32_t *d_idx, int K,
+                                  double *d_sums, double *d_counts, void *d_workspace, size_t workspace_bytes,
+                                  void *stream);
 /* q[i] = cb[idx[i]]  (cb_func.quantize after fpc_kmeans_assign_accumulate filled idx) */
 int fpc_kmeans_gather(const double *d_cb, int K, const int32_t *d_idx, long N, double *d_q, void *stream);
 

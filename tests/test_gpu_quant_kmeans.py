@@ -100,6 +100,81 @@ def test_kmeans_vs_reference_golden(torch_cuda, oracle):
     np.testing.assert_allclose(cbt, g["train_cb"], rtol=CENTROID_RTOL, atol=1e-300)
 
 
+def test_ordered_update_equals_the_reference_bit_for_bit(torch_cuda, oracle, synth):
+    """ordered=True: per-centroid float64 sums in data order (cb_func.py:82-86) -> `update`, the chained `vq_train`
+    schedule and the two-stage loop of train_cb.py return the reference's codebooks to the last bit."""
+    from quantization import cb_func
+    import fpc_train
+    torch = torch_cuda
+    g = load_golden("kmeans")
+    cb1 = cb_func.update(g["data"], g["cb0"], 64, verbose=False, ordered=True)
+    assert np.array_equal(cb1, g["cb1"])
+    cb2 = cb_func.update(g["data"], cb1, 64, verbose=False, ordered=True)
+    assert np.array_equal(cb2, g["cb2"])
+    np.random.seed(int(g["train_seed"]))
+    cbt = cb_func.vq_train(g["train_data"], np.zeros((8, 17)), 8, ordered=True)
+    assert np.array_equal(cbt, g["train_cb"])
+    # train_cb.py:191-211, first batch (vq_train per stage) and a later batch (10 x update per stage): the second stage
+    # runs on the float64 residual quantize(cb, r) - r
+    gs = load_golden("kmeans_stages")
+    data = torch.from_numpy(gs["data"]).cuda()
+    n_entries = [int(k) for k in gs["n_entries"]]
+    first = fpc_train.train_stages(data, n_entries, rng=np.random.RandomState(int(gs["train_seed"])), ordered=True)
+    later = fpc_train.train_stages(data, n_entries, codebooks=[gs["first_cb0"], gs["first_cb1"]], first_batch=False, ordered=True)
+    for i in range(2):
+        assert np.array_equal(first[i], gs["first_cb%d" % i]), "first batch, stage %d" % i
+        assert np.array_equal(later[i], gs["later_cb%d" % i]), "later batch, stage %d" % i
+    # larger seeded sets against the oracle: ragged sizes (tile = 2048 rows), tiny and full codebooks, float64 vectors,
+    # heavy skew (one centroid owns half the set), empty centroids
+    for n, K, seed in ((1, 1, 1), (2047, 3, 2), (2049, 7, 3), (300001, 1024, 4), (150000, 1000, 5), (70001, 512, 6)):
+        data = synth.make_kmeans_data(n, seed=seed, n_components=max(2, min(K, 64)))
+        if seed == 4:
+            data[::2] = data[0] * 0.5                     # skew + exact duplicates (ties broken by the lower index)
+        if seed == 6:
+            data = data.astype(np.float64) * (1.0 + 2.0 ** -30)          # a later stage's float64 vectors
+        cb = np.random.RandomState(seed).randn(K, 17) * 0.1
+        cb[K // 2] = 50.0                                 # nobody's nearest: an empty centroid -> the zero vector
+        want = oracle.kmeans_update(data, cb)
+        got = cb_func.update(data, cb, K, verbose=False, ordered=True)
+        assert np.array_equal(got, want), (n, K)
+        if K > 1:
+            assert np.all(got[K // 2] == 0.0)
+        again = cb_func.update(torch.from_numpy(data).cuda(), cb, K, verbose=False, ordered=True)
+        assert np.array_equal(again, got)
+        loose = cb_func.update(data, cb, K, verbose=False, ordered=False)
+        # the atomics path: the same sums in another order (a coordinate that cancels to ~1e-7 keeps 1e-18 absolute)
+        np.testing.assert_allclose(loose, want, rtol=CENTROID_RTOL, atol=1e-15)
+
+
+def test_ordered_update_full_size_is_reproducible(torch_cuda, synth):
+    """BASELINE's k-means size class (8 M vectors here, K = 1024): two ordered iterations give the same bits, the
+    counts add up to N, and the atomics path agrees to 1e-12."""
+    from quantization import cb_func
+    torch = torch_cuda
+    n, K = 8_000_000, 1024
+    g = torch.Generator(device="cuda").manual_seed(7)
+    data = torch.randn((n, 17), generator=g, device="cuda", dtype=torch.float32) * 0.1
+    cb = torch.from_numpy(np.random.RandomState(7).randn(K, 17) * 0.1).cuda()
+    a, sa, _ = cb_func.update_device(data, cb, ordered=True)
+    b, sb, _ = cb_func.update_device(data, cb, ordered=True)
+    c, sc, _ = cb_func.update_device(data, cb, ordered=False)
+    torch.cuda.synchronize()
+    assert torch.equal(a, b) and torch.equal(sa, sb)
+    assert float(sa[4]) == n and float(sc[4]) == n
+    np.testing.assert_allclose(c.cpu().numpy(), a.cpu().numpy(), rtol=CENTROID_RTOL, atol=1e-15)
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
+    ev[0].record()
+    for _ in range(5):
+        cb_func.update_device(data, cb, ordered=True)
+    ev[1].record()
+    for _ in range(5):
+        cb_func.update_device(data, cb, ordered=False)
+    ev[2].record()
+    torch.cuda.synchronize()
+    print("update on %d vectors, K = %d: ordered %.2f ms, atomics %.2f ms per iteration"
+          % (n, K, ev[0].elapsed_time(ev[1]) / 5, ev[1].elapsed_time(ev[2]) / 5))
+
+
 def test_colsum_is_numpy_float32_mean(torch_cuda, synth):
     """np.mean(data, 0) of float32 data, bit for bit (cb_func.py:34): row-order float32 additions, float32 division."""
     import fpc_native as N

@@ -18,6 +18,8 @@
 //
 // Algorithmic bytes per vector: idx 4 B read twice, perm 4 B written and read, the vector (68 B float32) read once
 // = 84 B, plus K * 4 B of tile counts per 2048 rows (2 B per vector at K = 1024), written once and read twice.
+#include <cstdlib>
+
 #include "fpc_common.cuh"
 
 namespace fpc {
@@ -30,7 +32,7 @@ constexpr int kOrdGroups = 256;         // tile groups of the two-level scan
 
 struct OrdPlan {
     long tiles, tiles_per_group;
-    size_t off_cnt, off_gtot, off_coff, off_perm, bytes;
+    size_t off_cnt, off_gtot, off_coff, off_cur, off_perm, bytes;
 };
 
 static OrdPlan ord_plan(long N, int K)
@@ -43,6 +45,7 @@ static OrdPlan ord_plan(long N, int K)
     p.off_cnt = o;  o += (size_t)p.tiles * K * sizeof(unsigned);          o = (o + 255) & ~(size_t)255;
     p.off_gtot = o; o += (size_t)kOrdGroups * K * sizeof(unsigned);       o = (o + 255) & ~(size_t)255;
     p.off_coff = o; o += (size_t)(K + 1) * sizeof(unsigned);              o = (o + 255) & ~(size_t)255;
+    p.off_cur = o;  o += (size_t)K * sizeof(unsigned);                    o = (o + 255) & ~(size_t)255;
     p.off_perm = o; o += (size_t)N * sizeof(unsigned);                    o = (o + 255) & ~(size_t)255;
     p.bytes = o;
     return p;
@@ -256,6 +259,121 @@ __global__ void __launch_bounds__(128) ord_sum_kernel(const TD *__restrict__ dat
     if (lane == 0) counts[k] += (double)(e - b);
 }
 
+// The same sums as a sweep over L2-sized blocks of rows (one launch per block).  A centroid's rows are scattered over
+// the whole set, so ord_sum_kernel gathers 68-byte rows straight from DRAM (96-128 bytes fetched per row, no page
+// locality).  Here every launch first pulls the NEXT block of rows into L2 with coalesced prefetches (streaming DRAM
+// traffic) and then every centroid adds its rows of THIS block, which the previous launch left in L2; the running sum
+// and the position in the centroid's row list are carried in global memory (float64, exact) from launch to launch.
+constexpr size_t kOrdBlockBytes = (size_t)32 << 20;
+
+// Streams [p, p + bytes) through L2 with real 16-byte loads (a prefetch instruction is a hint that a busy memory
+// system drops; these are not).  `first`, `count`: this CTA's position among the CTAs that share the range.
+__device__ __forceinline__ void ord_prefetch_range(const char *p, size_t bytes, unsigned first, unsigned count, unsigned *sink)
+{
+    const uintptr_t a0 = (reinterpret_cast<uintptr_t>(p) + 15) & ~(uintptr_t)15;
+    const uintptr_t a1 = (reinterpret_cast<uintptr_t>(p) + bytes) & ~(uintptr_t)15;
+    if (bytes < 32 || a1 <= a0) return;
+    const uint4 *q = reinterpret_cast<const uint4 *>(a0);
+    const size_t n = (a1 - a0) / 16;
+    unsigned x = 0u;
+    for (size_t l = (size_t)first * blockDim.x + threadIdx.x; l < n; l += (size_t)count * blockDim.x) {
+        uint4 v;
+        asm volatile("ld.global.cg.v4.u32 {%0, %1, %2, %3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(q + l));
+        x ^= v.x ^ v.y ^ v.z ^ v.w;
+    }
+    if (x == 0x9e3779b9u && bytes == 1) *sink = x;        // never true: keeps the loads
+}
+
+__global__ void ord_prefetch_kernel(const char *p, size_t bytes, const unsigned *__restrict__ coff, unsigned *__restrict__ cur, int K)
+{
+    ord_prefetch_range(p, bytes, blockIdx.x, gridDim.x, cur);
+    for (int k = blockIdx.x * blockDim.x + threadIdx.x; k < K; k += gridDim.x * blockDim.x) cur[k] = coff[k];
+}
+
+template <typename TD>
+__global__ void __launch_bounds__(128) ord_sum_block_kernel(const TD *__restrict__ data, const unsigned *__restrict__ perm,
+                                                            const unsigned *__restrict__ coff, unsigned *__restrict__ cur, int K,
+                                                            double *__restrict__ sums, double *__restrict__ counts,
+                                                            unsigned row_end, const char *next, size_t next_bytes, int last,
+                                                            unsigned sum_ctas)
+{
+    if (blockIdx.x >= sum_ctas) {           // the CTAs behind the centroids' stream the NEXT block of rows into L2
+        ord_prefetch_range(next, next_bytes, blockIdx.x - sum_ctas, gridDim.x - sum_ctas, cur);
+        return;
+    }
+    const int lane = threadIdx.x & 31;
+    const int warp = __shfl_sync(0xffffffffu, (int)(threadIdx.x >> 5), 0);
+    const int k = blockIdx.x * (blockDim.x >> 5) + warp;
+    if (k >= K) return;
+    const unsigned i0 = __shfl_sync(0xffffffffu, cur[k], 0), e = __shfl_sync(0xffffffffu, coff[k + 1], 0);
+    const int d = lane < kOrdDim ? lane : 0;
+    double acc = sums[(size_t)k * kOrdDim + d];
+    auto rows_at = [&](unsigned c) -> unsigned {          // row numbers of chunk c from the cursor; past the list: no row
+        const unsigned i = i0 + c * 32u + lane;
+        return i < e ? perm[i] : 0xffffffffu;
+    };
+    // rows of this block: the list is ascending, so they are a prefix of the chunk
+    auto inside = [&](unsigned rows) -> unsigned { return (unsigned)__popc(__ballot_sync(0xffffffffu, rows < row_end)); };
+    auto fetch = [&](TD (&v)[32], unsigned mine) {
+        if (mine >= row_end) mine = 0u;                   // not of this block: row 0, loaded and not added
+#pragma unroll
+        for (int j = 0; j < 32; ++j) {
+            const unsigned row = __shfl_sync(0xffffffffu, mine, j);
+            v[j] = data[(size_t)row * kOrdDim + d];
+        }
+    };
+    auto add = [&](const TD (&v)[32], unsigned n) {
+        if (n == 32u) {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) acc += (double)v[j];                  // ascending row order, float64: cb_func.py:86
+        } else {
+#pragma unroll
+            for (int j = 0; j < 32; ++j) if ((unsigned)j < n) acc += (double)v[j];
+        }
+    };
+    // NB register buffers of 32 rows: chunk c + NB - 1 is loaded while chunk c is added; the loop is unrolled over
+    // U = 4 steps so that no buffer is ever copied, and the row numbers of a chunk are read U steps before its loads.
+    constexpr int NB = sizeof(TD) == 4 ? 4 : 2;
+    constexpr int U = 4;
+    TD buf[NB][32];
+    unsigned cn[NB], mrow[U], total = 0u;
+#pragma unroll
+    for (int u = 0; u < NB; ++u) cn[u] = 0u;
+#pragma unroll
+    for (int u = 0; u < NB - 1; ++u) {
+        const unsigned r = rows_at(u);
+        cn[u] = inside(r);
+        if (cn[u]) fetch(buf[u], r);
+    }
+#pragma unroll
+    for (int u = 0; u < U; ++u) mrow[u] = rows_at(NB - 1 + u);
+    bool done = cn[0] == 0u;
+    for (unsigned c = 0; !done; c += U) {
+#pragma unroll
+        for (int u = 0; u < U; ++u) {
+            if (!done) {
+                const unsigned cc = c + u;                                // the chunk added in this step: buf[u % NB]
+                const unsigned ahead = cn[u % NB] == 32u ? inside(mrow[u]) : 0u;      // chunk cc + NB - 1
+                if (ahead) fetch(buf[(u + NB - 1) % NB], mrow[u]);
+                mrow[u] = rows_at(cc + NB - 1 + U);
+                add(buf[u % NB], cn[u % NB]);
+                total += cn[u % NB];
+                done = cn[u % NB] < 32u;
+                cn[(u + NB - 1) % NB] = ahead;
+                if (!done && cn[(u + 1) % NB] == 0u) done = true;
+            }
+        }
+    }
+    const unsigned i1 = i0 + total;
+    if (!last && lane < 4 && i1 + lane * 32u < e)          // the row numbers the next launch starts with
+        asm volatile("prefetch.global.L2 [%0];" ::"l"(perm + i1 + lane * 32u));
+    if (lane < kOrdDim) sums[(size_t)k * kOrdDim + lane] = acc;
+    if (lane == 0) {
+        cur[k] = i1;
+        if (last) counts[k] += (double)(e - coff[k]);
+    }
+}
+
 template <typename TD>
 static int accumulate_ordered(const TD *d_data, long N, const int32_t *d_idx, int K, double *d_sums, double *d_counts,
                               void *d_ws, size_t ws_bytes, cudaStream_t st)
@@ -282,8 +400,36 @@ static int accumulate_ordered(const TD *d_data, long N, const int32_t *d_idx, in
     FPC_LAUNCH_CHECK();
     ord_scatter_kernel<<<(unsigned)ctas, kOrdWarps * 32, smem, st>>>(d_idx, N, K, p.tiles, p.tiles_per_group, cnt, gtot, coff, perm);
     FPC_LAUNCH_CHECK();
-    ord_sum_kernel<TD><<<(K + 3) / 4, 128, 0, st>>>(d_data, perm, coff, K, d_sums, d_counts);
+    // FPC_KMEANS_ORDERED_VARIANT=g: the one-pass gather (ord_sum_kernel) instead of the blocked sweep, for A/B.
+    // (Also measured and dropped: one cp.async.bulk per row into a shared-memory ring -- 10.7 ms, the copy engine's
+    // fixed cost per 80-byte copy; 4-byte cp.async per lane -- 7.5 ms.)
+    static const char *variant = getenv("FPC_KMEANS_ORDERED_VARIANT");
+    if (variant != nullptr && variant[0] == 'g') {
+        ord_sum_kernel<TD><<<(K + 3) / 4, 128, 0, st>>>(d_data, perm, coff, K, d_sums, d_counts);
+        FPC_LAUNCH_CHECK();
+        return FPC_OK;
+    }
+    unsigned *cur = reinterpret_cast<unsigned *>(ws + p.off_cur);
+    const long block_rows = (long)(kOrdBlockBytes / (kOrdDim * sizeof(TD)));
+    const long blocks = (N + block_rows - 1) / block_rows;
+    const char *base = reinterpret_cast<const char *>(d_data);
+    const size_t row_bytes = kOrdDim * sizeof(TD);
+    auto span = [&](long blk) -> size_t {                 // bytes of block blk (0 past the end)
+        if (blk >= blocks) return 0;
+        const long r0 = blk * block_rows, r1 = (blk + 1) * block_rows < N ? (blk + 1) * block_rows : N;
+        return (size_t)(r1 - r0) * row_bytes;
+    };
+    ord_prefetch_kernel<<<148 * 2, 256, 0, st>>>(base, span(0), coff, cur, K);
     FPC_LAUNCH_CHECK();
+    for (long blk = 0; blk < blocks; ++blk) {
+        const long r1 = (blk + 1) * block_rows < N ? (blk + 1) * block_rows : N;
+        const unsigned sum_ctas = (unsigned)(K + 3) / 4;
+        const unsigned pf_ctas = span(blk + 1) ? 148u * 2u : 0u;
+        ord_sum_block_kernel<TD><<<sum_ctas + pf_ctas, 128, 0, st>>>(d_data, perm, coff, cur, K, d_sums, d_counts, (unsigned)r1,
+                                                                     base + (size_t)(blk + 1) * block_rows * row_bytes, span(blk + 1),
+                                                                     blk + 1 == blocks, sum_ctas);
+        FPC_LAUNCH_CHECK();
+    }
     return FPC_OK;
 }
 

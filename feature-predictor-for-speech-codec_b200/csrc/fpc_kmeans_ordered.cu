@@ -30,6 +30,15 @@ constexpr int kOrdTileRows = 2048;      // rows of one warp's tile
 constexpr int kOrdWarps = 4;            // warps per CTA of the tile kernels (kOrdWarps * K counters in shared memory)
 constexpr int kOrdGroups = 256;         // tile groups of the two-level scan
 
+// acc += v[0] + ... + v[31] in order, in float64.  (Measured and dropped: widening float32 -> float64 on the integer
+// pipe instead of F2F.F64.F32 -- 245 registers and 8.3 ms instead of 5.6.)
+template <typename TD>
+__device__ __forceinline__ void ord_add32(double &acc, const TD (&v)[32])
+{
+#pragma unroll
+    for (int j = 0; j < 32; ++j) acc += (double)v[j];
+}
+
 struct OrdPlan {
     long tiles, tiles_per_group;
     size_t off_cnt, off_gtot, off_coff, off_cur, off_perm, bytes;
@@ -199,14 +208,26 @@ __global__ void __launch_bounds__(128) ord_sum_kernel(const TD *__restrict__ dat
     const unsigned b = __shfl_sync(0xffffffffu, coff[k], 0), e = __shfl_sync(0xffffffffu, coff[k + 1], 0);
     const int d = lane < kOrdDim ? lane : 0;
     double acc = sums[(size_t)k * kOrdDim + d];
-    constexpr unsigned kOrdAhead = 12;
+    constexpr unsigned kOrdAhead = 12;      // chunks between the L2 prefetch of a row and its load
+    constexpr unsigned kRowsAhead = 24;     // chunks between the copy of a chunk's row numbers and their first use
+    constexpr unsigned kRowRing = 32;
     constexpr int NB = sizeof(TD) == 4 ? 4 : 2;
     const unsigned nc = (e - b + 31u) / 32u;
     const unsigned left = (e - b) & 31u;
-    auto rows_at = [&](unsigned c) -> unsigned {                          // row numbers of chunk c, one per lane
+    // Row numbers: ncu's source page showed half of the stall samples waiting for perm[] (read 4 steps ahead into
+    // registers).  They now travel through a shared-memory ring, copied kRowsAhead chunks ahead by cp.async (one 4-byte
+    // copy per lane and chunk; each lane reads back only what it copied itself).
+    __shared__ unsigned s_rows[4][kRowRing][32];
+    auto rows_issue = [&](unsigned c) {
         const unsigned i = b + c * 32u + lane;
-        return (c < nc && i < e) ? perm[i] : 0xffffffffu;
+        unsigned *dst = &s_rows[warp][c % kRowRing][lane];
+        if (c < nc && i < e)
+            asm volatile("cp.async.ca.shared.global [%0], [%1], 4;" ::"r"(smem_u32(dst)), "l"(perm + i) : "memory");
+        else
+            *dst = 0xffffffffu;
+        asm volatile("cp.async.commit_group;" ::: "memory");
     };
+    auto rows_get = [&](unsigned c) -> unsigned { return s_rows[warp][c % kRowRing][lane]; };
     auto pull = [&](unsigned row) {
         if (row != 0xffffffffu) {
             const char *p0 = reinterpret_cast<const char *>(data + (size_t)row * kOrdDim);
@@ -223,31 +244,25 @@ __global__ void __launch_bounds__(128) ord_sum_kernel(const TD *__restrict__ dat
             v[j] = data[(size_t)row * kOrdDim + d];
         }
     };
-    constexpr int U = 4;                    // steps per loop body; row numbers are loaded U steps before they are used
-    unsigned mrow[U], farr[U];
-#pragma unroll
-    for (int u = 0; u < U; ++u) { mrow[u] = 0xffffffffu; farr[u] = 0xffffffffu; }
+    constexpr int U = 4;                    // steps per loop body (a multiple of NB: no buffer is ever copied)
     if (nc > 0) {
-        for (unsigned q = NB; q <= kOrdAhead; ++q) pull(rows_at(q));
+        for (unsigned q = 0; q < kRowsAhead; ++q) rows_issue(q);
+        asm volatile("cp.async.wait_group 0;" ::: "memory");
+        for (unsigned q = NB - 1; q <= kOrdAhead; ++q) pull(rows_get(q));
 #pragma unroll
-        for (int u = 0; u < U; ++u) { mrow[u] = rows_at(NB - 1 + u); farr[u] = rows_at(kOrdAhead + 1 + u); }
-#pragma unroll
-        for (int u = 0; u < NB - 1; ++u) fetch(buf[u], rows_at(u));
+        for (int u = 0; u < NB - 1; ++u) fetch(buf[u], rows_get(u));
     }
     for (unsigned c = 0; c < nc; c += U) {
 #pragma unroll
         for (int u = 0; u < U; ++u) {
             const unsigned cc = c + u;                                    // the chunk added in this step: buf[u % NB]
             if (cc < nc) {
-                if (cc + NB - 1 < nc) fetch(buf[(u + NB - 1) % NB], mrow[u]);
-                mrow[u] = rows_at(cc + NB - 1 + U);
-                pull(farr[u]);
-                farr[u] = rows_at(cc + kOrdAhead + 1 + U);
-                if (lane == 0 && b + (cc + 3 * kOrdAhead) * 32u < e)       // the row numbers themselves, far ahead
-                    asm volatile("prefetch.global.L2 [%0];" ::"l"(perm + b + (cc + 3 * kOrdAhead) * 32u));
+                rows_issue(cc + kRowsAhead);
+                asm volatile("cp.async.wait_group %0;" ::"n"(kRowsAhead - kOrdAhead - 1) : "memory");   // chunk cc + kOrdAhead + 1 is here
+                if (cc + NB - 1 < nc) fetch(buf[(u + NB - 1) % NB], rows_get(cc + NB - 1));
+                pull(rows_get(cc + kOrdAhead + 1));
                 if (cc + 1 < nc || left == 0u) {
-#pragma unroll
-                    for (int j = 0; j < 32; ++j) acc += (double)buf[u % NB][j];     // ascending row order, float64: cb_func.py:86
+                    ord_add32(acc, buf[u % NB]);                          // ascending row order, float64: cb_func.py:86
                 } else {
 #pragma unroll
                     for (int j = 0; j < 32; ++j) if ((unsigned)j < left) acc += (double)buf[u % NB][j];
@@ -255,6 +270,7 @@ __global__ void __launch_bounds__(128) ord_sum_kernel(const TD *__restrict__ dat
             }
         }
     }
+    asm volatile("cp.async.wait_group 0;" ::: "memory");
     if (lane < kOrdDim) sums[(size_t)k * kOrdDim + lane] = acc;
     if (lane == 0) counts[k] += (double)(e - b);
 }
@@ -324,8 +340,7 @@ __global__ void __launch_bounds__(128) ord_sum_block_kernel(const TD *__restrict
     };
     auto add = [&](const TD (&v)[32], unsigned n) {
         if (n == 32u) {
-#pragma unroll
-            for (int j = 0; j < 32; ++j) acc += (double)v[j];                  // ascending row order, float64: cb_func.py:86
+            ord_add32(acc, v);                                                 // ascending row order, float64: cb_func.py:86
         } else {
 #pragma unroll
             for (int j = 0; j < 32; ++j) if ((unsigned)j < n) acc += (double)v[j];

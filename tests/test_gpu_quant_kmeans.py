@@ -130,6 +130,14 @@ def test_ordered_update_equals_the_reference_bit_for_bit(torch_cuda, oracle, syn
         data = synth.make_kmeans_data(n, seed=seed, n_components=max(2, min(K, 64)))
         if seed == 4:
             data[::2] = data[0] * 0.5                     # skew + exact duplicates (ties broken by the lower index)
+        if seed == 5:
+            # zeros of both signs, denormals, the smallest normal float and a tiny normal one
+            data[7::101, 3] = 0.0
+            data[11::103, 4] = -0.0
+            data[13::107, 5] = 1e-40
+            data[17::109, 6] = -1.4e-45
+            data[19::113, 7] = np.float32(1.17549435e-38)
+            data[23::127, 8] = np.float32(2.0 ** -100)
         if seed == 6:
             data = data.astype(np.float64) * (1.0 + 2.0 ** -30)          # a later stage's float64 vectors
         cb = np.random.RandomState(seed).randn(K, 17) * 0.1

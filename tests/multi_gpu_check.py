@@ -94,6 +94,20 @@ def main():
             ref = O.kmeans_update(data, ref)
         np.testing.assert_allclose(mine, ref, rtol=1e-11, atol=1e-300)
         print("k-means: 3 sharded Lloyd iterations on %d ranks match the oracle to 1e-11; ranks agree bit for bit" % world)
+    # ordered sums (data order inside every shard, then the all-reduce): the same bits on every rank and on every run
+    runs = []
+    for _ in range(2):
+        co = torch.from_numpy(cb0).to(dev)
+        for _ in range(3):
+            co, _, _ = cb_func.update_device(shard, co, ordered=True)
+        runs.append(co)
+    assert torch.equal(runs[0], runs[1]), "ordered update: two runs differ"
+    allco = [torch.empty_like(co) for _ in range(world)]
+    dist.all_gather(allco, runs[0])
+    assert all(torch.equal(a, runs[0]) for a in allco), "ordered update: ranks disagree"
+    if rank == 0:
+        np.testing.assert_allclose(runs[0].cpu().numpy(), ref, rtol=1e-11, atol=1e-300)
+        print("k-means ordered: reproducible run to run, ranks agree, oracle to 1e-11")
     # seeded vq_train: jitter broadcast from rank 0
     np.random.seed(1234 + rank)          # ranks deliberately seeded differently: rank 0's draw must win
     small = torch.from_numpy(data[first:first + cnt][:2000]).to(dev)

@@ -48,6 +48,14 @@ def test_argument_validation_without_gpu():
     assert L.fpc_kmeans_assign_accumulate(None, 0, None, 4, None, None, None, None, 0, None) == 0   # N == 0
     assert L.fpc_kmeans_assign_accumulate(dummy, 5, dummy, 4096, dummy, dummy, None, None, 0, None) == 3
     assert L.fpc_scl_quantize(dummy, 3, dummy, 0, 1000, dummy, dummy, None) == 3       # > 256 levels
+    # ordered sums (cb_func.py:82-86 in data order): sizes this build does not take, empty shard, short workspace
+    assert L.fpc_kmeans_ordered_workspace_bytes(-1, 8) == 0 and L.fpc_kmeans_ordered_workspace_bytes(10, 4096) == 0
+    need = L.fpc_kmeans_ordered_workspace_bytes(100_000, 1024)
+    assert need >= 100_000 * 4 + 49 * 1024 * 4           # the row permutation + one count per (2048-row tile, centroid)
+    assert L.fpc_kmeans_accumulate_ordered(dummy, 0, 5, dummy, 4096, dummy, dummy, dummy, need, None) == 2    # K > 2048
+    assert L.fpc_kmeans_accumulate_ordered(None, 0, 0, None, 8, dummy, dummy, None, 0, None) == 0              # N == 0
+    assert L.fpc_kmeans_accumulate_ordered(dummy, 0, 5, dummy, 8, None, None, dummy, need, None) == 1
+    assert L.fpc_kmeans_accumulate_ordered(dummy, 0, 100_000, dummy, 1024, dummy, dummy, dummy, 16, None) == 4
     cb = N.Codebooks()
     cb.vq, cb.vq_dtype, cb.vq_stages, cb.vq_entries = 16, 0, 3, 64                      # 3 stages: vq_func.py:111 raises
     assert L.fpc_pack_codebooks(ctypes.byref(cb), dummy, L.fpc_packed_codebooks_bytes(), None) == 3
